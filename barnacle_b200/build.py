@@ -1,0 +1,81 @@
+"""Builds barnacle_b200/lib/libbarnacle_b200.so (sm_100a only) in-tree.
+
+    python -m barnacle_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  Flags that matter for parity:
+  -fmad=false            no implicit FMA contraction in device code
+  (nvcc defaults)        -prec-div=true -prec-sqrt=true -ftz=false
+  -ffp-contract=off      same for the host-side C++
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libbarnacle_b200.so")
+OBJ_DIR = os.path.join(HERE, "lib", "obj")
+
+NVCC = os.environ.get("BN_NVCC", "/usr/local/cuda/bin/nvcc")
+HOST_CXX = "g++"  # /usr/bin/g++ (the CXX the image exports lacks libgomp.spec / is not needed here)
+
+HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-mavx2", "-mfma", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra",
+              "-I/usr/local/cuda/include"]
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "-ccbin", HOST_CXX]
+
+HOST_SOURCES = ["host/error.cpp", "host/scene_host.cpp", "cuda/scene_convert.cpp"]
+CUDA_SOURCES = ["cuda/kernels.cu"]
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def _all_inputs() -> list[str]:
+    out = []
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for dp, _, fs in os.walk(root):
+            out += [os.path.join(dp, f) for f in fs if f.endswith((".h", ".hpp", ".cuh", ".cu", ".cpp"))]
+    out.append(os.path.abspath(__file__))
+    return out
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and _newer(LIB, _all_inputs()):
+        return LIB
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace("/", "_") + ".o")
+        cmd = [HOST_CXX, *HOST_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        _run(cmd, verbose)
+        objs.append(obj)
+    for src in CUDA_SOURCES:
+        obj = os.path.join(OBJ_DIR, src.replace("/", "_") + ".o")
+        cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", os.path.join(CSRC, src), "-o", obj]
+        _run(cmd, verbose)
+        objs.append(obj)
+    cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static"]
+    _run(cmd, verbose)
+    return LIB
+
+
+def _run(cmd: list[str], verbose: bool) -> None:
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0 or verbose:
+        sys.stdout.write(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError(f"build step failed: {' '.join(cmd)}")
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv or "--verbose" in sys.argv))

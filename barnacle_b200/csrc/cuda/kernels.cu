@@ -1,0 +1,681 @@
+// Wavefront path tracer for sm_100a: the kernels and the C-ABI entry points
+// that replace ProgressiveIntegrator.Render + PathTracingIntegrator.Li
+// (Base/Integrator.fs:22-55, Extensions/Integrator/PathTracing.fs:14-81).
+//
+// One "wave" = (a range of 8x4 pixel blocks) x (a range of sample ids), at most
+// `wave_capacity` camera paths.  Per wave:
+//   raygen                        -> compacted path state (bounce 0)
+//   for bounce in 0..maxDepth-1:  extend (closest hit) -> shade -> shadow (any hit + connect)
+//   accumulate                    -> film[pix] = fma(1/spp, L, film[pix]) in sample order
+// Kernels are persistent (grid = SMs x resident CTAs); warps fetch 32 queue
+// entries at a time from a global cursor and append to the next queue with
+// warp-aggregated atomics.  All paths of a wave are at the same depth, so the
+// reference's `depth` is the bounce index.
+//
+// Compiled with -fmad=false (see vecmath.cuh).  No tensor cores: nothing here is
+// a dense contraction.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/barnacle_b200.h"
+#include "device_scene.h"
+#include "scene_convert.h"
+#include "shade.cuh"
+#include "traverse.cuh"
+#include "vecmath.cuh"
+
+namespace bnhost {
+void set_error(const std::string& msg);
+}
+
+namespace bn {
+
+constexpr int kBlock = 128;
+
+struct WaveParams {
+  int width, height;
+  int spp, max_depth, rr_depth, frame_id;
+  int x0, y0, x1, y1;
+  int nbx;            // 8x4 pixel blocks per row of the window
+  int block_begin;    // first pixel block of this wave
+  int n_blocks;       // pixel blocks in this wave
+  int sample_begin;   // first sampleId of this wave
+  int n_samples;      // samples per pixel in this wave
+  uint32_t flags;
+  float inv_spp;
+};
+
+// ---- warp helpers --------------------------------------------------------------
+BN_DEV int lane_id() { return threadIdx.x & 31; }
+
+// Each warp claims 32 consecutive queue entries.
+BN_DEV int warp_fetch(int* cursor) {
+  int base = 0;
+  if (lane_id() == 0) base = atomicAdd(cursor, 32);
+  return __shfl_sync(0xffffffffu, base, 0);
+}
+// Warp-aggregated append: one atomicAdd per warp.  Must be called by all 32 lanes.
+BN_DEV int warp_append(int* counter, bool pred) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  int base = 0;
+  if (lane_id() == 0 && m) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+
+BN_DEV void wave_pixel(const WaveParams& wp, int pl, int& x, int& y) {
+  const int block = wp.block_begin + (pl >> 5);
+  const int lane = pl & 31;
+  x = wp.x0 + (block % wp.nbx) * 8 + (lane & 7);
+  y = wp.y0 + (block / wp.nbx) * 4 + (lane >> 3);
+}
+
+// ---- raygen: RenderTile's sample loop head (Integrator.fs:34-39) ------------------
+__global__ void __launch_bounds__(kBlock) k_raygen(DScene sc, WaveParams wp, float4* __restrict__ s0, float4* __restrict__ s1,
+                                                   float4* __restrict__ s2, float4* __restrict__ rad, int* n_active) {
+  const int npw = wp.n_blocks * 32;
+  const int total = npw * wp.n_samples;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < total; base += gridDim.x * blockDim.x) {
+    const int pid = base + lane_id();
+    bool alive = false;
+    float3 o = splat(0.f), d = splat(0.f);
+    uint32_t rng = 0;
+    if (pid < total) {
+      rad[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int sl = pid / npw, pl = pid - sl * npw;
+      int x, y;
+      wave_pixel(wp, pl, x, y);
+      if (x < wp.x1 && y < wp.y1) {
+        alive = true;
+        rng = xxhash32_three((uint32_t)x, (uint32_t)y, (uint32_t)(wp.frame_id * wp.spp + wp.sample_begin + sl));
+        const float upx = lcg(rng), upy = lcg(rng);  // Next2D: X then Y (Sampler.fs:16)
+        const float ulx = lcg(rng), uly = lcg(rng);
+        primary_ray(sc.cam, wp.width, wp.height, x, y, upx, upy, ulx, uly, o, d);
+      }
+    }
+    const int pos = warp_append(n_active, alive);
+    if (alive) {
+      s0[pos] = make_float4(o.x, o.y, o.z, d.x);
+      s1[pos] = make_float4(d.y, d.z, 1.f, 1.f);  // beta = 1
+      s2[pos] = make_float4(1.f, 0.f, __uint_as_float(rng), __int_as_float(pid));
+    }
+  }
+}
+
+// ---- extend: closest hit for every live path ----------------------------------------
+__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, const float4* __restrict__ s0, const float4* __restrict__ s1,
+                                                   float4* __restrict__ hits, const int* __restrict__ n_ptr, int* cursor) {
+  const int n = *n_ptr;
+  for (;;) {
+    const int base = warp_fetch(cursor);
+    if (base >= n) break;
+    const int i = base + lane_id();
+    if (i < n) {
+      const float4 a = s0[i], b = s1[i];
+      float t = CUDART_INF_F;  // PathTracing.fs:25
+      HitRec h;
+      trace<false>(sc, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), t, h);
+      hits[i] = make_float4(t, __int_as_float(h.inst), __int_as_float(h.prim), 0.f);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- shade: one iteration of Li's loop body (PathTracing.fs:30-79) --------------------
+__global__ void __launch_bounds__(kBlock) k_shade(DScene sc, WaveParams wp, int bounce, const float4* __restrict__ s0, const float4* __restrict__ s1,
+                                                  const float4* __restrict__ s2, const float4* __restrict__ hits, float4* __restrict__ o0,
+                                                  float4* __restrict__ o1, float4* __restrict__ o2, float4* __restrict__ q0, float4* __restrict__ q1,
+                                                  float4* __restrict__ q2, float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr,
+                                                  int* n_out, int* n_shadow, int* cursor, unsigned long long* shadow_ref) {
+  const int n = *n_ptr;
+  for (;;) {
+    const int base = warp_fetch(cursor);
+    if (base >= n) break;
+    const int i = base + lane_id();
+    bool alive = false, has_shadow = false, ref_shadow = false;
+    float3 P = splat(0.f), nd = splat(0.f), beta = splat(0.f);
+    float bs_pdf = 0.f;
+    uint32_t rng = 0;
+    int pid = 0;
+    float3 sh_wi = splat(0.f), sh_a = splat(0.f), sh_b = splat(0.f);
+    float sh_tmax = 0.f;
+    if (i < n) {
+      const float4 a = s0[i], b = s1[i], c = s2[i], h = hits[i];
+      const float3 o = f3(a.x, a.y, a.z), d = f3(a.w, b.x, b.y);
+      beta = f3(b.z, b.w, c.x);
+      const float prev_pdf = c.y;
+      rng = __float_as_uint(c.z);
+      pid = __float_as_int(c.w);
+      const float t = h.x;
+      const int inst = __float_as_int(h.y), prim = __float_as_int(h.z);
+      if (inst >= 0) {
+        const float4* hp = reinterpret_cast<const float4*>(sc.inst_head + inst);
+        const float4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
+        const uint32_t kind_prim = __float_as_uint(h0.w);
+        const int material = __float_as_int(h1.w), light = __float_as_int(h2.x);
+        const Mat43 W2O = load_mat43(reinterpret_cast<const float4*>(sc.inst_w2o + inst));
+        const Mat43 O2W = load_mat43(reinterpret_cast<const float4*>(sc.inst_o2w + inst));
+        // rebuild the interaction exactly as the intersection routines produced it
+        const float3 oo = transform_point(o, W2O), od = transform_dir(d, W2O);
+        const float3 pobj = point_at(oo, od, t);
+        float3 nobj;
+        const bool is_sphere = (kind_prim & 0x80000000u) != 0u;
+        if (is_sphere) {  // Sphere.fs:50-62 / 64-75 (normal flipped on the near root only)
+          nobj = normalize(pobj);
+          if (prim == 0 && dot(nobj, od) > 0.f) nobj = -nobj;
+        } else {          // Mesh.fs:76-78
+          const GMesh* mesh = sc.meshes + kind_prim;
+          const float4 m2 = __ldg(reinterpret_cast<const float4*>(mesh) + 2);
+          float3 p0, p1, p2;
+          load_tri(sc.tris + __float_as_uint(m2.x) + prim, p0, p1, p2);
+          nobj = normalize(cross(p1 - p0, p2 - p0));
+        }
+        // LocalGeometry.Transform (Primitive.fs:57-58)
+        P = transform_point(pobj, O2W);
+        const Onb onb = transform_onb(onb_from_n(nobj), O2W);
+
+        if (light >= 0) {  // PathTracing.fs:30-40 + UniformLightSampler.Eval (Uniform.fs:40-49)
+          const float3 wo = normalize(o - P);
+          const float cos_wo = dot(onb.n, wo);
+          float pdf_surface;
+          if (is_sphere) {  // SphereInstance.EvalPDF, Sphere.fs:115-126
+            const float radius = h2.y;
+            const float j = length(cross(transform_dir(onb.t, W2O), transform_dir(onb.b, W2O)));
+            pdf_surface = j / (4.f * kPi * radius * radius);
+          } else {          // MeshInstance.EvalPDF with tag = 0 (Mesh.fs:300-304), host-precomputed
+            pdf_surface = h2.y;
+          }
+          const float dist2 = length_sq(o - P);
+          const float3 Le = light_eval(load_light(sc, light), dot(wo, onb.n));
+          const float lpdf = dist2 * pdf_surface / (net_max(fabsf(cos_wo), 1e-6f) * (float)sc.n_light_inst);
+          const float w = bounce == 0 ? 1.f : prev_pdf * (1.f / (lpdf + prev_pdf));
+          const float4 L4 = rad[pid];
+          const float3 L = vfma(beta, Le * w, f3(L4.x, L4.y, L4.z));
+          rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
+        }
+        if (material >= 0) {
+          const GMaterial mat = load_material(sc, material);
+          const float usel = lcg(rng);
+          const float ulx = lcg(rng), uly = lcg(rng);
+          const LightSampleRec ls = light_sampler_sample(sc, P, usel, ulx, uly);  // PathTracing.fs:43
+          const float dist = length(ls.p - P);
+          const float3 wo_l = world_to_local(onb, -d);
+          if (ls.pdf != 0.f) {  // :47-59
+            ref_shadow = true;
+            const BsdfEval fe = material_eval(mat, wo_l, world_to_local(onb, ls.wi));
+            sh_a = beta * fe.bsdf;
+            sh_b = ls.L * (1.f / (fe.pdf + ls.pdf));
+            // fma(0, finite, L) == L bit for bit: the connection cannot change the image
+            const bool null_contrib = sh_a.x == 0.f && sh_a.y == 0.f && sh_a.z == 0.f && isfinite(sh_b.x) && isfinite(sh_b.y) && isfinite(sh_b.z);
+            has_shadow = !null_contrib || (wp.flags & BN_RENDER_TRACE_NULL_SHADOW);
+            sh_wi = ls.wi;
+            sh_tmax = dist - 1e-3f;
+          }
+          const float ulobe = lcg(rng);
+          const float ubx = lcg(rng), uby = lcg(rng);
+          const BsdfSample bs = material_sample(mat, wo_l, ulobe, ubx, uby);  // :61
+          if (bs.eval.pdf != 0.f) {
+            nd = local_to_world(onb, bs.wi);
+            beta = beta * bs.eval.bsdf * (1.f / bs.eval.pdf);
+            bs_pdf = bs.eval.pdf;
+            bool cont = true;
+            if (bounce >= wp.rr_depth) {  // :69-75
+              const float q = net_min(1.f, net_max(beta.x, net_max(beta.y, beta.z)));
+              if (lcg(rng) < q) beta = beta * (1.f / q);
+              else cont = false;
+            }
+            alive = cont && (bounce + 1 < wp.max_depth);
+          }
+        }
+      }
+    }
+    const int pos = warp_append(n_out, alive);
+    if (alive) {
+      o0[pos] = make_float4(P.x, P.y, P.z, nd.x);
+      o1[pos] = make_float4(nd.y, nd.z, beta.x, beta.y);
+      o2[pos] = make_float4(beta.z, bs_pdf, __uint_as_float(rng), __int_as_float(pid));
+    }
+    const int spos = warp_append(n_shadow, has_shadow);
+    if (has_shadow) {
+      q0[spos] = make_float4(P.x, P.y, P.z, sh_wi.x);
+      q1[spos] = make_float4(sh_wi.y, sh_wi.z, sh_tmax, __int_as_float(pid));
+      q2[spos] = make_float4(sh_a.x, sh_a.y, sh_a.z, sh_b.x);
+      q3[spos] = make_float4(sh_b.y, sh_b.z, 0.f, 0.f);
+    }
+    const unsigned rm = __ballot_sync(0xffffffffu, ref_shadow);
+    if (lane_id() == 0 && rm) atomicAdd(shadow_ref, (unsigned long long)__popc(rm));
+  }
+}
+
+// ---- shadow: any hit + connect (PathTracing.fs:47-59) ----------------------------------
+__global__ void __launch_bounds__(kBlock) k_shadow(DScene sc, const float4* __restrict__ q0, const float4* __restrict__ q1, const float4* __restrict__ q2,
+                                                   const float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr, int* cursor) {
+  const int n = *n_ptr;
+  for (;;) {
+    const int base = warp_fetch(cursor);
+    if (base >= n) break;
+    const int i = base + lane_id();
+    if (i < n) {
+      const float4 a = q0[i], b = q1[i];
+      float t = b.z;
+      HitRec h;
+      if (!trace<true>(sc, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), t, h)) {
+        const float4 c = q2[i], e = q3[i];
+        const int pid = __float_as_int(b.w);
+        const float4 L4 = rad[pid];
+        const float3 L = vfma(f3(c.x, c.y, c.z), f3(c.w, e.x, e.y), f3(L4.x, L4.y, L4.z));
+        rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- accumulate: accum = fma(1/spp, radiance, accum); Film.SetPixel -------------------
+// (Integrator.fs:41-44, Film.fs:41-46).  One thread per pixel walks its samples in
+// sampleId order, continuing the chain left in the film by earlier waves.
+__global__ void __launch_bounds__(kBlock) k_accumulate(WaveParams wp, const float4* __restrict__ rad, float* __restrict__ film) {
+  const int npw = wp.n_blocks * 32;
+  for (int pl = blockIdx.x * blockDim.x + threadIdx.x; pl < npw; pl += gridDim.x * blockDim.x) {
+    int x, y;
+    wave_pixel(wp, pl, x, y);
+    if (x >= wp.x1 || y >= wp.y1) continue;
+    float* px = film + ((size_t)(wp.height - y - 1) * wp.width + x) * 3;
+    float3 acc = f3(px[0], px[1], px[2]);
+    for (int s = 0; s < wp.n_samples; ++s) {
+      const float4 L = rad[(size_t)s * npw + pl];
+      const float3 radiance = f3(L.x, L.y, L.z) * (1.f / 1.f);  // * rcp(camera pdf), pdf == 1 (Pinhole.fs:27)
+      acc = vfma(splat(wp.inv_spp), radiance, acc);
+    }
+    px[0] = acc.x; px[1] = acc.y; px[2] = acc.z;
+  }
+}
+
+// per-path radiance export (bn_render_radiance): [sample][(y-y0)*rw + (x-x0)][3]
+__global__ void __launch_bounds__(kBlock) k_export_radiance(WaveParams wp, const float4* __restrict__ rad, float* __restrict__ out, int sample_origin) {
+  const int npw = wp.n_blocks * 32;
+  const int total = npw * wp.n_samples;
+  const int rw = wp.x1 - wp.x0, rh = wp.y1 - wp.y0;
+  for (int pid = blockIdx.x * blockDim.x + threadIdx.x; pid < total; pid += gridDim.x * blockDim.x) {
+    const int sl = pid / npw, pl = pid - sl * npw;
+    int x, y;
+    wave_pixel(wp, pl, x, y);
+    if (x >= wp.x1 || y >= wp.y1) continue;
+    const float4 L = rad[pid];
+    float* o = out + (((size_t)(wp.sample_begin + sl - sample_origin) * rh + (y - wp.y0)) * rw + (x - wp.x0)) * 3;
+    o[0] = L.x; o[1] = L.y; o[2] = L.z;
+  }
+}
+
+// ---- fixed-batch traversal (bn_trace) -------------------------------------------------
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock) k_trace(DScene sc, const BnRay* __restrict__ rays, unsigned long long n, BnHit* __restrict__ hits, unsigned long long* cursor) {
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(cursor, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const unsigned long long i = base + lane_id();
+    if (i < n) {
+      const BnRay r = rays[i];
+      const float3 o = f3(r.origin[0], r.origin[1], r.origin[2]), d = f3(r.direction[0], r.direction[1], r.direction[2]);
+      float t = r.tmax;
+      HitRec h;
+      const bool hit = trace<ANY>(sc, o, d, t, h);
+      BnHit out;
+      if (ANY) {
+        out.t = 0.f; out.u = 0.f; out.v = 0.f; out.instance = hit ? 1 : 0; out.primitive = 0;
+      } else {
+        out.t = t; out.u = h.u; out.v = h.v; out.instance = h.inst; out.primitive = h.prim;
+        if (hit) {
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.inst_head + h.inst));
+          if (__float_as_uint(h0.w) & 0x80000000u) {  // sphere uv (Sphere.fs:55-56), libdevice atan2/acos
+            const Mat43 M = load_mat43(reinterpret_cast<const float4*>(sc.inst_w2o + h.inst));
+            const float3 nn = normalize(point_at(transform_point(o, M), transform_dir(d, M), t));
+            out.u = atan2f(nn.z, nn.x) / (2.f * kPi) + 0.5f;
+            out.v = acosf(nn.y) / kPi;
+            out.primitive = 0;
+          }
+        }
+      }
+      hits[i] = out;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace bn
+
+// =================================================================================
+// host side of the C ABI
+// =================================================================================
+using namespace bn;
+
+struct BnScene {
+  int device = 0;
+  int num_sms = 0;
+  DScene d{};
+  std::vector<void*> allocs;
+  // wave buffers
+  size_t cap = 0;
+  float4* state[2] = {nullptr, nullptr};  // 3 planes each
+  float4* hits = nullptr;
+  float4* shq = nullptr;                  // 4 planes
+  float4* rad = nullptr;
+  int* counters = nullptr;
+  size_t counters_len = 0;
+  unsigned long long* shadow_ref = nullptr;
+  float* film = nullptr;
+  size_t film_len = 0;
+  bool poisoned = false;
+};
+
+namespace {
+
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  bnhost::set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return false;
+}
+#define BN_CUDA(call)                                  \
+  do {                                                 \
+    if (!cuda_ok((call), #call)) return BN_ERR_CUDA;   \
+  } while (0)
+
+template <class T>
+int upload(BnScene* s, const std::vector<T>& v, const T** out) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  BN_CUDA(cudaMalloc(&p, bytes));
+  s->allocs.push_back(p);
+  if (!v.empty()) BN_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<const T*>(p);
+  return BN_OK;
+}
+
+size_t wave_capacity_paths() {
+  const char* e = std::getenv("BN_WAVE_PATHS");
+  size_t v = e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)4 << 20;
+  v = std::max<size_t>(v, 1024);
+  return (v + 31) & ~(size_t)31;
+}
+
+int ensure_wave_buffers(BnScene* s, size_t cap) {
+  if (s->cap >= cap) return BN_OK;
+  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad})
+    if (p) cudaFree(p);
+  s->cap = 0;
+  BN_CUDA(cudaMalloc((void**)&s->state[0], cap * 3 * sizeof(float4)));
+  BN_CUDA(cudaMalloc((void**)&s->state[1], cap * 3 * sizeof(float4)));
+  BN_CUDA(cudaMalloc((void**)&s->hits, cap * sizeof(float4)));
+  BN_CUDA(cudaMalloc((void**)&s->shq, cap * 4 * sizeof(float4)));
+  BN_CUDA(cudaMalloc((void**)&s->rad, cap * sizeof(float4)));
+  s->cap = cap;
+  return BN_OK;
+}
+
+int validate_params(const BnRenderParams* p) {
+  if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth < 0 || p->sample_begin < 0 || p->sample_end > p->spp ||
+      p->sample_begin > p->sample_end || p->x0 < 0 || p->y0 < 0 || p->x1 > p->width || p->y1 > p->height || p->x0 > p->x1 || p->y0 > p->y1) {
+    bnhost::set_error("bn_render: invalid BnRenderParams");
+    return BN_ERR_INVALID;
+  }
+  return BN_OK;
+}
+
+// Runs every wave of the window.  If d_radiance != nullptr the per-path radiance is
+// exported instead of accumulated into the film.
+int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_radiance, cudaStream_t stream, BnStats* stats) {
+  if (s->poisoned) { bnhost::set_error("scene is unusable after an earlier CUDA error"); return BN_ERR_CUDA; }
+  if (s->d.n_light_inst == 0) { bnhost::set_error("LightSamplerBase: No light primitives found."); return BN_ERR_NO_LIGHT; }
+  BN_CUDA(cudaSetDevice(s->device));
+  const int rw = p->x1 - p->x0, rh = p->y1 - p->y0, ns = p->sample_end - p->sample_begin;
+  const int nbx = (rw + 7) / 8, nby = (rh + 3) / 4;
+  const long long total_blocks = (long long)nbx * nby;
+  uint64_t launches = 0;
+  cudaEvent_t ev0, ev1;
+  BN_CUDA(cudaEventCreate(&ev0));
+  BN_CUDA(cudaEventCreate(&ev1));
+  if (d_film) BN_CUDA(cudaMemsetAsync(d_film, 0, sizeof(float) * 3 * (size_t)p->width * p->height, stream));
+  BN_CUDA(cudaEventRecord(ev0, stream));
+  uint64_t n_paths = 0;
+  std::vector<int> h_counters;
+  if (total_blocks > 0 && ns > 0 && p->max_depth > 0) {
+    const size_t cap_target = wave_capacity_paths();
+    long long blocks_per_wave = std::min<long long>(total_blocks, std::max<long long>(1, (long long)(cap_target / 32)));
+    int samples_per_wave = (int)std::max<long long>(1, std::min<long long>(ns, (long long)cap_target / (blocks_per_wave * 32)));
+    const size_t cap = (size_t)blocks_per_wave * 32 * samples_per_wave;
+    int rc = ensure_wave_buffers(s, cap);
+    if (rc != BN_OK) return rc;
+    const long long n_block_chunks = (total_blocks + blocks_per_wave - 1) / blocks_per_wave;
+    const long long n_sample_chunks = (ns + samples_per_wave - 1) / samples_per_wave;
+    const long long n_waves = n_block_chunks * n_sample_chunks;
+    // per wave: [0] n_active(bounce 0..maxDepth) | n_shadow(bounce) | cursors 3 per bounce
+    const int D = p->max_depth;
+    const size_t per_wave = (size_t)(D + 1) + D + 3 * (size_t)D;
+    const size_t need = per_wave * (size_t)n_waves;
+    if (s->counters_len < need) {
+      if (s->counters) cudaFree(s->counters);
+      s->counters = nullptr; s->counters_len = 0;
+      BN_CUDA(cudaMalloc((void**)&s->counters, need * sizeof(int)));
+      s->counters_len = need;
+    }
+    BN_CUDA(cudaMemsetAsync(s->counters, 0, need * sizeof(int), stream));
+    BN_CUDA(cudaMemsetAsync(s->shadow_ref, 0, sizeof(unsigned long long), stream));
+    const int grid = s->num_sms * 8;
+    long long wave = 0;
+    for (long long bc = 0; bc < n_block_chunks; ++bc) {
+      for (long long scn = 0; scn < n_sample_chunks; ++scn, ++wave) {
+        WaveParams wp{};
+        wp.width = p->width; wp.height = p->height; wp.spp = p->spp; wp.max_depth = p->max_depth; wp.rr_depth = p->rr_depth;
+        wp.frame_id = p->frame_id; wp.x0 = p->x0; wp.y0 = p->y0; wp.x1 = p->x1; wp.y1 = p->y1; wp.nbx = nbx;
+        wp.block_begin = (int)(bc * blocks_per_wave);
+        wp.n_blocks = (int)std::min<long long>(blocks_per_wave, total_blocks - bc * blocks_per_wave);
+        wp.sample_begin = p->sample_begin + (int)(scn * samples_per_wave);
+        wp.n_samples = std::min(samples_per_wave, p->sample_end - wp.sample_begin);
+        wp.flags = p->flags;
+        wp.inv_spp = 1.0f / (float)p->spp;  // MathF.ReciprocalEstimate restated as IEEE 1/x
+        int* base = s->counters + per_wave * (size_t)wave;
+        int* n_active = base;
+        int* n_shadow = base + (D + 1);
+        int* cursors = base + (D + 1) + D;
+        const size_t cp = s->cap;
+        float4* A = s->state[0];
+        float4* B = s->state[1];
+        k_raygen<<<grid, kBlock, 0, stream>>>(s->d, wp, A, A + cp, A + 2 * cp, s->rad, n_active);
+        ++launches;
+        for (int b = 0; b < D; ++b) {
+          k_extend<<<grid, kBlock, 0, stream>>>(s->d, A, A + cp, s->hits, n_active + b, cursors + 3 * b);
+          k_shade<<<grid, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
+                                               s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b, n_active + b + 1, n_shadow + b,
+                                               cursors + 3 * b + 1, s->shadow_ref);
+          k_shadow<<<grid, kBlock, 0, stream>>>(s->d, s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b, cursors + 3 * b + 2);
+          launches += 3;
+          std::swap(A, B);
+        }
+        if (d_radiance) k_export_radiance<<<grid, kBlock, 0, stream>>>(wp, s->rad, d_radiance, p->sample_begin);
+        else k_accumulate<<<grid, kBlock, 0, stream>>>(wp, s->rad, d_film);
+        ++launches;
+      }
+    }
+    BN_CUDA(cudaGetLastError());
+    h_counters.resize(need);
+    BN_CUDA(cudaEventRecord(ev1, stream));
+    BN_CUDA(cudaMemcpyAsync(h_counters.data(), s->counters, need * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { s->poisoned = true; cuda_ok(e, "render waves"); return BN_ERR_CUDA; }
+    if (stats) {
+      uint64_t ext = 0, sh = 0;
+      for (long long w = 0; w < n_waves; ++w) {
+        const int* base = h_counters.data() + per_wave * (size_t)w;
+        n_paths += (uint64_t)base[0];
+        for (int b = 0; b < D; ++b) { ext += (uint64_t)base[b]; sh += (uint64_t)base[D + 1 + b]; }
+      }
+      unsigned long long ref = 0;
+      BN_CUDA(cudaMemcpy(&ref, s->shadow_ref, sizeof ref, cudaMemcpyDeviceToHost));
+      stats->paths = n_paths; stats->extend_rays = ext; stats->shadow_rays = sh; stats->shadow_rays_ref = ref;
+    }
+  } else {
+    BN_CUDA(cudaEventRecord(ev1, stream));
+    BN_CUDA(cudaStreamSynchronize(stream));
+    if (stats) { stats->paths = 0; stats->extend_rays = 0; stats->shadow_rays = 0; stats->shadow_rays_ref = 0; }
+  }
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    stats->gpu_ms = ms;
+    stats->kernel_launches = launches;
+    stats->extend_ms = stats->shade_ms = stats->shadow_ms = stats->other_ms = 0.0;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  return BN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
+  if (!desc || !out) { bnhost::set_error("bn_scene_create: NULL argument"); return BN_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = bn_device_count();
+  if (ndev <= 0) { bnhost::set_error("no CUDA device available (the hot path has no CPU fallback)"); return BN_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) { bnhost::set_error("bn_scene_create: device ordinal out of range"); return BN_ERR_INVALID; }
+  bnconv::ConvertedScene cs;
+  std::string err;
+  if (!bnconv::convert_scene(*desc, cs, err)) { bnhost::set_error(err); return BN_ERR_INVALID; }
+  BN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  BN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { bnhost::set_error("device is not sm_100-class (this library is built for sm_100a only)"); return BN_ERR_NO_DEVICE; }
+  auto* s = new BnScene();
+  s->device = device;
+  s->num_sms = prop.multiProcessorCount;
+  int rc = BN_OK;
+  DScene& d = s->d;
+  if ((rc = upload(s, cs.nodes, &d.nodes)) || (rc = upload(s, cs.inst_head, &d.inst_head)) || (rc = upload(s, cs.inst_w2o, &d.inst_w2o)) ||
+      (rc = upload(s, cs.inst_o2w, &d.inst_o2w)) || (rc = upload(s, cs.meshes, &d.meshes)) || (rc = upload(s, cs.tris, &d.tris)) ||
+      (rc = upload(s, cs.alias, &d.alias)) || (rc = upload(s, cs.sphere_radii, &d.sphere_radii)) || (rc = upload(s, cs.materials, &d.materials)) ||
+      (rc = upload(s, cs.lights, &d.lights)) || (rc = upload(s, cs.light_inst, &d.light_inst))) {
+    bn_scene_destroy(s);
+    return rc;
+  }
+  d.tlas = cs.tlas;
+  d.n_inst = (uint32_t)cs.inst_head.size();
+  d.n_light_inst = (uint32_t)cs.light_inst.size();
+  d.cam = cs.cam;
+  if (cudaMalloc((void**)&s->shadow_ref, sizeof(unsigned long long)) != cudaSuccess) { bn_scene_destroy(s); bnhost::set_error("cudaMalloc failed"); return BN_ERR_CUDA; }
+  *out = s;
+  return BN_OK;
+}
+
+void bn_scene_destroy(BnScene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->counters, (void*)s->shadow_ref, (void*)s->film})
+    if (p) cudaFree(p);
+  delete s;
+}
+
+int bn_render_device(BnScene* s, const BnRenderParams* p, void* d_film, void* stream, BnStats* stats) {
+  if (!s || !d_film) { bnhost::set_error("bn_render_device: NULL argument"); return BN_ERR_INVALID; }
+  int rc = validate_params(p);
+  if (rc != BN_OK) return rc;
+  return render_waves(s, p, static_cast<float*>(d_film), nullptr, static_cast<cudaStream_t>(stream), stats);
+}
+
+int bn_render(BnScene* s, const BnRenderParams* p, float* film, BnStats* stats) {
+  if (!s || !film) { bnhost::set_error("bn_render: NULL argument"); return BN_ERR_INVALID; }
+  int rc = validate_params(p);
+  if (rc != BN_OK) return rc;
+  BN_CUDA(cudaSetDevice(s->device));
+  const size_t len = (size_t)p->width * p->height * 3;
+  if (s->film_len < len) {
+    if (s->film) cudaFree(s->film);
+    s->film = nullptr; s->film_len = 0;
+    BN_CUDA(cudaMalloc((void**)&s->film, len * sizeof(float)));
+    s->film_len = len;
+  }
+  rc = render_waves(s, p, s->film, nullptr, nullptr, stats);
+  if (rc != BN_OK) return rc;
+  BN_CUDA(cudaMemcpy(film, s->film, len * sizeof(float), cudaMemcpyDeviceToHost));
+  return BN_OK;
+}
+
+int bn_render_radiance(BnScene* s, const BnRenderParams* p, float* radiance) {
+  if (!s || !radiance) { bnhost::set_error("bn_render_radiance: NULL argument"); return BN_ERR_INVALID; }
+  int rc = validate_params(p);
+  if (rc != BN_OK) return rc;
+  BN_CUDA(cudaSetDevice(s->device));
+  const size_t len = (size_t)(p->x1 - p->x0) * (p->y1 - p->y0) * (p->sample_end - p->sample_begin) * 3;
+  if (len == 0) return BN_OK;
+  float* d = nullptr;
+  BN_CUDA(cudaMalloc((void**)&d, len * sizeof(float)));
+  rc = render_waves(s, p, nullptr, d, nullptr, nullptr);
+  if (rc == BN_OK && !cuda_ok(cudaMemcpy(radiance, d, len * sizeof(float), cudaMemcpyDeviceToHost), "copy radiance")) rc = BN_ERR_CUDA;
+  cudaFree(d);
+  return rc;
+}
+
+int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, void* d_hits, void* stream_v, float* ms) {
+  if (!s || (n && (!d_rays || !d_hits))) { bnhost::set_error("bn_trace_device: NULL argument"); return BN_ERR_INVALID; }
+  if (s->poisoned) { bnhost::set_error("scene is unusable after an earlier CUDA error"); return BN_ERR_CUDA; }
+  BN_CUDA(cudaSetDevice(s->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  unsigned long long* cursor = nullptr;
+  BN_CUDA(cudaMalloc((void**)&cursor, sizeof(unsigned long long)));
+  BN_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
+  cudaEvent_t e0, e1;
+  BN_CUDA(cudaEventCreate(&e0));
+  BN_CUDA(cudaEventCreate(&e1));
+  BN_CUDA(cudaEventRecord(e0, stream));
+  const int grid = s->num_sms * 8;
+  if (n) {
+    if (any_hit) k_trace<true><<<grid, kBlock, 0, stream>>>(s->d, static_cast<const BnRay*>(d_rays), n, static_cast<BnHit*>(d_hits), cursor);
+    else k_trace<false><<<grid, kBlock, 0, stream>>>(s->d, static_cast<const BnRay*>(d_rays), n, static_cast<BnHit*>(d_hits), cursor);
+  }
+  BN_CUDA(cudaEventRecord(e1, stream));
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  float t = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(cursor);
+  if (e != cudaSuccess) { s->poisoned = true; cuda_ok(e, "bn_trace"); return BN_ERR_CUDA; }
+  if (ms) *ms = t;
+  return BN_OK;
+}
+
+int bn_trace(BnScene* s, const BnRay* rays, uint64_t n, int any_hit, BnHit* hits) {
+  if (!s || (n && (!rays || !hits))) { bnhost::set_error("bn_trace: NULL argument"); return BN_ERR_INVALID; }
+  if (n == 0) return BN_OK;
+  BN_CUDA(cudaSetDevice(s->device));
+  BnRay* d_rays = nullptr;
+  BnHit* d_hits = nullptr;
+  BN_CUDA(cudaMalloc((void**)&d_rays, n * sizeof(BnRay)));
+  if (!cuda_ok(cudaMalloc((void**)&d_hits, n * sizeof(BnHit)), "cudaMalloc hits")) { cudaFree(d_rays); return BN_ERR_CUDA; }
+  int rc = BN_OK;
+  if (!cuda_ok(cudaMemcpy(d_rays, rays, n * sizeof(BnRay), cudaMemcpyHostToDevice), "copy rays")) rc = BN_ERR_CUDA;
+  if (rc == BN_OK) rc = bn_trace_device(s, d_rays, n, any_hit, d_hits, nullptr, nullptr);
+  if (rc == BN_OK && !cuda_ok(cudaMemcpy(hits, d_hits, n * sizeof(BnHit), cudaMemcpyDeviceToHost), "copy hits")) rc = BN_ERR_CUDA;
+  cudaFree(d_rays);
+  cudaFree(d_hits);
+  return rc;
+}
+
+}  // extern "C"

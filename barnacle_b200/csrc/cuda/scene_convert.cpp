@@ -1,0 +1,203 @@
+// Host-side conversion of the reference-layout scene into the traversal layout.
+// Compiled by g++ with -ffp-contract=off: the one arithmetic result produced
+// here (MeshInstance.EvalPDF for tag 0, Mesh.fs:300-304) must have the bits the
+// reference's op sequence gives.
+#include "scene_convert.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "../host/host_math.hpp"
+#include "traverse_limits.h"
+
+namespace bnconv {
+namespace {
+
+using bnhost::V3;
+
+struct TreeOut {
+  bn::GTree tree;
+  int depth = 0;
+  int max_leaf = 0;
+};
+
+bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_t node_base, std::vector<bn::GNode>& out, TreeOut& t, std::string& err,
+                const char* what) {
+  if (count == 0) { err = std::string(what) + ": empty BVH"; return false; }
+  std::vector<int> gidx(count, -1);
+  int next = 0;
+  for (uint32_t i = 0; i < count; ++i)
+    if (!n[i].is_leaf) gidx[i] = next++;
+  auto leaf_ref = [&](uint32_t i, uint32_t& ref) {
+    int c = n[i].count, first = n[i].right_or_offset;
+    if (c <= 0 || c > bn::kMaxLeafCount) { err = std::string(what) + ": leaf item count out of range (1.." + std::to_string(bn::kMaxLeafCount) + ")"; return false; }
+    if (first < 0 || (uint32_t)first + (uint32_t)c > item_count || (uint32_t)first >= bn::kMaxLeafFirst) { err = std::string(what) + ": leaf item range out of bounds"; return false; }
+    ref = bn::kLeafBit | ((uint32_t)c << 24) | (uint32_t)first;
+    if (c > t.max_leaf) t.max_leaf = c;
+    return true;
+  };
+  auto child_ref = [&](uint32_t c, uint32_t& ref) {
+    if (n[c].is_leaf) return leaf_ref(c, ref);
+    ref = (uint32_t)gidx[c];
+    return true;
+  };
+  out.resize(node_base + (size_t)next);
+  // depth via explicit stack (preorder array: left = i+1, right = RightChild)
+  std::vector<std::pair<uint32_t, int>> stack{{0u, 1}};
+  std::vector<char> seen(count, 0);
+  while (!stack.empty()) {
+    auto [i, depth] = stack.back();
+    stack.pop_back();
+    if (i >= count || seen[i]) { err = std::string(what) + ": malformed BVH (node visited twice or out of range)"; return false; }
+    seen[i] = 1;
+    if (depth > t.depth) t.depth = depth;
+    if (n[i].is_leaf) continue;
+    int r = n[i].right_or_offset;
+    uint32_t l = i + 1;
+    if (l >= count || r <= (int)l || (uint32_t)r >= count) { err = std::string(what) + ": malformed BVH (child index)"; return false; }
+    if (n[i].split_axis < 0 || n[i].split_axis > 2) { err = std::string(what) + ": split axis out of range"; return false; }
+    bn::GNode g;
+    std::memcpy(g.lmin, n[l].bounds_min, 12); std::memcpy(g.lmax, n[l].bounds_max, 12);
+    std::memcpy(g.rmin, n[r].bounds_min, 12); std::memcpy(g.rmax, n[r].bounds_max, 12);
+    if (!child_ref(l, g.left) || !child_ref((uint32_t)r, g.right)) return false;
+    g.axis = (uint32_t)n[i].split_axis;
+    g.pad = 0;
+    out[node_base + (size_t)gidx[i]] = g;
+    stack.push_back({l, depth + 1});
+    stack.push_back({(uint32_t)r, depth + 1});
+  }
+  std::memcpy(t.tree.bmin, n[0].bounds_min, 12);
+  std::memcpy(t.tree.bmax, n[0].bounds_max, 12);
+  t.tree.node_base = node_base;
+  if (n[0].is_leaf) { if (!leaf_ref(0, t.tree.root)) return false; }
+  else t.tree.root = 0;
+  return true;
+}
+
+void mat43(const float* m, bn::GMat43& o) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 3; ++c) o.m[r * 3 + c] = m[r * 4 + c];
+}
+
+}  // namespace
+
+bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) {
+  if (!d.tlas_nodes || !d.instances || d.instance_count == 0) { err = "scene has no instances / TLAS"; return false; }
+  if ((d.mesh_count && !d.meshes) || (d.vertex_count && !d.vertices) || (d.triangle_count && !d.triangles) || (d.blas_node_count && !d.blas_nodes) ||
+      (d.alias_count && !d.alias) || (d.sphere_count && !d.sphere_radii) || (d.material_count && !d.materials) || (d.light_count && !d.lights) ||
+      (d.light_instance_count && !d.light_instances)) {
+    err = "scene description has a NULL array with a non-zero count";
+    return false;
+  }
+  TreeOut tl;
+  if (!build_tree(d.tlas_nodes, d.tlas_node_count, d.instance_count, 0, out.nodes, tl, err, "TLAS")) return false;
+  out.tlas = tl.tree;
+  int max_blas_depth = 0;
+  // meshes
+  out.meshes.resize(d.mesh_count);
+  out.tris.resize(d.triangle_count);
+  for (uint32_t m = 0; m < d.mesh_count; ++m) {
+    const BnMesh& mm = d.meshes[m];
+    if ((uint64_t)mm.vertex_offset + mm.vertex_count > d.vertex_count || (uint64_t)mm.tri_offset + mm.tri_count > d.triangle_count ||
+        (uint64_t)mm.node_offset + mm.node_count > d.blas_node_count || (uint64_t)mm.alias_offset + mm.tri_count > d.alias_count || mm.tri_count == 0) {
+      err = "mesh slice out of range";
+      return false;
+    }
+    TreeOut bt;
+    if (!build_tree(d.blas_nodes + mm.node_offset, mm.node_count, mm.tri_count, (uint32_t)out.nodes.size(), out.nodes, bt, err, "BLAS")) return false;
+    if (bt.depth > max_blas_depth) max_blas_depth = bt.depth;
+    if (bt.max_leaf > tl.max_leaf) {}
+    bn::GMesh& g = out.meshes[m];
+    g.tree = bt.tree;
+    g.tri_base = mm.tri_offset;
+    g.tri_count = mm.tri_count;
+    g.alias_base = mm.alias_offset;
+    g.pad = 0;
+    const float* v = d.vertices + (size_t)mm.vertex_offset * 3;
+    for (uint32_t t = 0; t < mm.tri_count; ++t) {
+      const int32_t* ix = d.triangles + ((size_t)mm.tri_offset + t) * 3;
+      bn::GTri& gt = out.tris[mm.tri_offset + t];
+      std::memset(&gt, 0, sizeof gt);
+      for (int k = 0; k < 3; ++k) {
+        if (ix[k] < 0 || (uint32_t)ix[k] >= mm.vertex_count) { err = "triangle vertex index out of range"; return false; }
+        float* dst = k == 0 ? gt.p0 : (k == 1 ? gt.p1 : gt.p2);
+        std::memcpy(dst, v + (size_t)ix[k] * 3, 12);
+      }
+    }
+  }
+  out.max_stack = tl.depth + tl.max_leaf + max_blas_depth + 2;
+  if (out.max_stack > bn::kStackSize) {
+    err = "scene needs a traversal stack of " + std::to_string(out.max_stack) + " entries (limit " + std::to_string(bn::kStackSize) + ")";
+    return false;
+  }
+  // instances
+  out.inst_head.resize(d.instance_count);
+  out.inst_w2o.resize(d.instance_count);
+  out.inst_o2w.resize(d.instance_count);
+  for (uint32_t i = 0; i < d.instance_count; ++i) {
+    const BnInstance& in = d.instances[i];
+    bn::GInstHead& h = out.inst_head[i];
+    std::memset(&h, 0, sizeof h);
+    std::memcpy(h.bmin, in.bounds_min, 12);
+    std::memcpy(h.bmax, in.bounds_max, 12);
+    if (in.material_id >= (int)d.material_count || in.light_id >= (int)d.light_count) { err = "instance material/light index out of range"; return false; }
+    h.material = in.material_id < 0 ? -1 : in.material_id;
+    h.light = in.light_id < 0 ? -1 : in.light_id;
+    mat43(in.world_to_object, out.inst_w2o[i]);
+    mat43(in.object_to_world, out.inst_o2w[i]);
+    if (in.prim_kind == BN_PRIM_SPHERE) {
+      if (in.prim_id >= d.sphere_count) { err = "instance sphere index out of range"; return false; }
+      h.kind_prim = 0x80000000u | in.prim_id;
+      h.light_pdf_area = d.sphere_radii[in.prim_id];
+    } else if (in.prim_kind == BN_PRIM_MESH) {
+      if (in.prim_id >= d.mesh_count) { err = "instance mesh index out of range"; return false; }
+      h.kind_prim = in.prim_id;
+      // MeshInstance.EvalPDF (Mesh.fs:300-304) for tag = 0:
+      // Table[0].pdf / SurfaceArea(Transform(triangle 0, ObjectToWorld))
+      const BnMesh& mm = d.meshes[in.prim_id];
+      const bn::GTri& t0 = out.tris[mm.tri_offset];
+      bnhost::M4 M;
+      std::memcpy(M.m, in.object_to_world, 64);
+      V3 p0 = bnhost::transform_point({t0.p0[0], t0.p0[1], t0.p0[2]}, M);
+      V3 p1 = bnhost::transform_point({t0.p1[0], t0.p1[1], t0.p1[2]}, M);
+      V3 p2 = bnhost::transform_point({t0.p2[0], t0.p2[1], t0.p2[2]}, M);
+      float area = 0.5f * bnhost::length(bnhost::cross(p1 - p0, p2 - p0));
+      h.light_pdf_area = d.alias[mm.alias_offset].pdf / area;
+    } else {
+      err = "unknown primitive kind";
+      return false;
+    }
+  }
+  out.light_inst.assign(d.light_instances, d.light_instances + d.light_instance_count);
+  for (uint32_t li : out.light_inst)
+    if (li >= d.instance_count || d.instances[li].light_id < 0) { err = "light instance list is inconsistent"; return false; }
+  out.alias.resize(d.alias_count);
+  for (uint32_t i = 0; i < d.alias_count; ++i) {
+    if (d.alias[i].alias < 0) { err = "alias entry out of range"; return false; }
+    out.alias[i] = {d.alias[i].alias, d.alias[i].prob, d.alias[i].pdf};
+  }
+  out.sphere_radii.assign(d.sphere_radii, d.sphere_radii + d.sphere_count);
+  out.materials.resize(d.material_count);
+  for (uint32_t i = 0; i < d.material_count; ++i) {
+    const BnMaterial& m = d.materials[i];
+    if (m.type > BN_MAT_PBR) { err = "unknown material type"; return false; }
+    out.materials[i] = {m.type, m.base_color[0], m.base_color[1], m.base_color[2], m.p0, m.p1, 0.f, 0.f};
+  }
+  out.lights.resize(d.light_count);
+  for (uint32_t i = 0; i < d.light_count; ++i) out.lights[i] = {d.lights[i].emission[0], d.lights[i].emission[1], d.lights[i].emission[2], d.lights[i].two_sided ? 1u : 0u};
+  // camera
+  const BnCamera& c = d.camera;
+  if (c.type > BN_CAM_THIN_LENS) { err = "unknown camera type"; return false; }
+  out.cam.type = c.type;
+  out.cam.viewport_h = 2.f * tanf(c.fov_y * 3.14159274101257324f / 360.f);  // Pinhole.fs:15
+  out.cam.aspect = c.aspect_ratio;
+  out.cam.aperture = c.aperture;
+  out.cam.focus = c.focus_distance;
+  out.cam.push_forward = c.push_forward;
+  bn::GMat43 cm;
+  mat43(c.camera_to_world, cm);
+  std::memcpy(out.cam.c2w, cm.m, sizeof cm.m);
+  return true;
+}
+
+}  // namespace bnconv

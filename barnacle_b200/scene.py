@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+Names follow the reference so call sites read like Barnacle's own:
+
+    scene = Scene.Load("scenes/cbox_pt.json")       # Extensions/Scene/Loader.fs:277-281
+    scene.Render(0.0, "out.png")                    # Extensions/Scene/Render.fs:10-19
+
+`Scene.Render` does what Render.fs does — Film.Clear, Scene.Traverse, BVHAggregate,
+UniformLightSampler (all inside the host-side builder), then the timed
+`Integrator.Render`, which here is `GpuPathTracingIntegrator.Render`: one C-ABI
+call into the CUDA wavefront (bn_render).  No PyTorch is needed on this path;
+torch is only used by the multi-GPU driver (barnacle_b200/multi_gpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import BarnacleError, BnHostSceneInfo, BnRenderParams, BnStats, check
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("tmax", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("instance", "<i4"), ("primitive", "<i4")])
+assert RAY_DTYPE.itemsize == 28 and HIT_DTYPE.itemsize == 20
+
+TONE_MAPPING = {0: "identity", 1: "aces", 2: "gamma"}
+INTEGRATORS = {0: "normal", 1: "direct", 2: "path-tracing", 3: "pssmlt"}
+
+
+@dataclass
+class RenderStats:
+    paths: int
+    extend_rays: int
+    shadow_rays: int
+    shadow_rays_ref: int
+    kernel_launches: int
+    gpu_ms: float
+
+    @property
+    def rays(self) -> int:
+        return self.extend_rays + self.shadow_rays
+
+
+def make_params(width, height, spp, max_depth=8, rr_depth=5, frame_id=0, sample_begin=0, sample_end=None,
+                rect=None, flags=0) -> BnRenderParams:
+    x0, y0, x1, y1 = rect if rect is not None else (0, 0, width, height)
+    return BnRenderParams(width, height, spp, max_depth, rr_depth, frame_id, sample_begin,
+                          spp if sample_end is None else sample_end, x0, y0, x1, y1, flags)
+
+
+class Film:
+    """Base/Film.fs: Pixels is Vector3[W*H], row 0 = top (SetPixel flips Y)."""
+
+    def __init__(self, width: int, height: int, tone_mapping: str = "identity"):
+        self.ImageWidth, self.ImageHeight, self.ToneMapping = width, height, tone_mapping
+        self.Pixels = np.zeros((height * width, 3), dtype=np.float32)
+
+    @property
+    def Resolution(self):
+        return (self.ImageWidth, self.ImageHeight)
+
+    def Clear(self):
+        self.Pixels[:] = 0
+
+    def image(self) -> np.ndarray:
+        return self.Pixels.reshape(self.ImageHeight, self.ImageWidth, 3)
+
+    def to_rgba8(self) -> np.ndarray:
+        lib = _ffi.load()
+        out = np.empty((self.ImageHeight, self.ImageWidth, 4), dtype=np.uint8)
+        tm = {v: k for k, v in TONE_MAPPING.items()}[self.ToneMapping]
+        check(lib.bn_host_film_to_rgba8(self.Pixels.ctypes.data, self.ImageWidth, self.ImageHeight, tm, out.ctypes.data), "Film.Save")
+        return out
+
+    def Save(self, filename: str):
+        """Film.Save (Film.fs:55-66): tone-map + clamp -> RGBA8 -> encoder chosen by extension."""
+        if filename.endswith(".npy"):
+            np.save(filename, self.image())
+            return
+        from PIL import Image
+        Image.fromarray(self.to_rgba8(), "RGBA").save(filename)
+
+
+class GpuScene:
+    """Device-resident scene (bn_scene_create) — the aggregate + light sampler + camera
+    the integrator reads, flattened."""
+
+    def __init__(self, desc_ptr, device: int = 0):
+        self._lib = _ffi.load()
+        h = C.c_void_p()
+        check(self._lib.bn_scene_create(desc_ptr, device, C.byref(h)), "bn_scene_create")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bn_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def _stats(st: BnStats) -> RenderStats:
+        return RenderStats(st.paths, st.extend_rays, st.shadow_rays, st.shadow_rays_ref, st.kernel_launches, st.gpu_ms)
+
+    def render(self, params: BnRenderParams, film: np.ndarray | None = None):
+        """bn_render: host film (W*H*3 fp32, Film.Pixels layout); returns (film, stats)."""
+        if film is None:
+            film = np.empty((params.height * params.width, 3), dtype=np.float32)
+        assert film.dtype == np.float32 and film.size == params.width * params.height * 3 and film.flags.c_contiguous
+        st = BnStats()
+        check(self._lib.bn_render(self._h, C.byref(params), film.ctypes.data, C.byref(st)), "bn_render")
+        return film, self._stats(st)
+
+    def render_device(self, params: BnRenderParams, d_film_ptr: int, stream: int = 0):
+        """bn_render_device: film is a device pointer on this scene's device."""
+        st = BnStats()
+        check(self._lib.bn_render_device(self._h, C.byref(params), C.c_void_p(d_film_ptr), C.c_void_p(stream), C.byref(st)), "bn_render_device")
+        return self._stats(st)
+
+    def render_radiance(self, params: BnRenderParams) -> np.ndarray:
+        ns = params.sample_end - params.sample_begin
+        out = np.empty((ns, params.y1 - params.y0, params.x1 - params.x0, 3), dtype=np.float32)
+        check(self._lib.bn_render_radiance(self._h, C.byref(params), out.ctypes.data), "bn_render_radiance")
+        return out
+
+    def trace(self, rays: np.ndarray, any_hit: bool = False) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        check(self._lib.bn_trace(self._h, rays.ctypes.data, rays.shape[0], 1 if any_hit else 0, hits.ctypes.data), "bn_trace")
+        return hits
+
+    def trace_device(self, d_rays: int, n: int, any_hit: bool, d_hits: int, stream: int = 0) -> float:
+        ms = C.c_float()
+        check(self._lib.bn_trace_device(self._h, C.c_void_p(d_rays), n, 1 if any_hit else 0, C.c_void_p(d_hits), C.c_void_p(stream), C.byref(ms)), "bn_trace_device")
+        return ms.value
+
+
+class GpuPathTracingIntegrator:
+    """Drop-in for PathTracingIntegrator (PathTracing.fs:9-12) whose Render
+    (Integrator.fs:46-55) runs on the GPU."""
+
+    def __init__(self, spp: int, max_depth: int = 8, rr_depth: int = 5):
+        self.SamplePerPixel, self.MaxDepth, self.RRDepth = spp, max_depth, rr_depth
+        self.FrameId = 0
+        self.last_stats: RenderStats | None = None
+
+    def Render(self, gpu_scene: GpuScene, film: Film, flags: int = 0):
+        p = make_params(film.ImageWidth, film.ImageHeight, self.SamplePerPixel, self.MaxDepth, self.RRDepth, self.FrameId, flags=flags)
+        _, self.last_stats = gpu_scene.render(p, film.Pixels)
+        self.FrameId += 1
+
+
+class Scene:
+    """Base/Scene.fs `Scene` + Loader.fs `Scene.Load` + Render.fs `Scene.Render`."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+        info = BnHostSceneInfo()
+        lib.bn_host_scene_info(handle, C.byref(info))
+        self.info = info
+        self.Film = Film(info.width, info.height, TONE_MAPPING[info.tone_mapping])
+        self.integrator_type = INTEGRATORS[info.integrator]
+        self.Integrator = GpuPathTracingIntegrator(info.spp, info.max_depth, info.rr_depth)
+        self._gpu: GpuScene | None = None
+
+    @staticmethod
+    def Load(filename: str, base_dir: str | None = None, time_: float = 0.0) -> "Scene":
+        lib = _ffi.load()
+        h = C.c_void_p()
+        bd = (base_dir or os.getcwd()).encode()
+        check(lib.bn_host_scene_load(filename.encode(), bd, C.c_float(time_), C.byref(h)), "Scene.Load")
+        return Scene(h, lib)
+
+    @staticmethod
+    def LoadString(text: str, base_dir: str | None = None, time_: float = 0.0) -> "Scene":
+        lib = _ffi.load()
+        h = C.c_void_p()
+        bd = (base_dir or os.getcwd()).encode()
+        check(lib.bn_host_scene_load_string(text.encode(), bd, C.c_float(time_), C.byref(h)), "Scene.Load")
+        return Scene(h, lib)
+
+    @property
+    def desc(self):
+        return self._lib.bn_host_scene_desc(self._h)
+
+    def instance_permutation(self) -> np.ndarray:
+        n = self.desc.contents.instance_count
+        return np.ctypeslib.as_array(self._lib.bn_host_scene_instance_permutation(self._h), (n,)).copy()
+
+    def triangle_permutation(self, mesh: int) -> np.ndarray:
+        n = self.desc.contents.meshes[mesh].tri_count
+        return np.ctypeslib.as_array(self._lib.bn_host_scene_triangle_permutation(self._h, mesh), (n,)).copy()
+
+    def gpu(self, device: int = 0) -> GpuScene:
+        if self._gpu is None or self._gpu.device != device:
+            self._gpu = GpuScene(self.desc, device)
+        return self._gpu
+
+    def Render(self, t: float, filename: str | None, device: int = 0) -> float:
+        """Render.fs:10-19.  Returns the seconds spent in Integrator.Render (the
+        reference's Stopwatch region)."""
+        if self.integrator_type != "path-tracing":
+            raise BarnacleError(f"integrator '{self.integrator_type}' is outside the GPU hot path (path-tracing only)")
+        self.Film.Clear()
+        gpu = self.gpu(device)
+        t0 = time.perf_counter()
+        self.Integrator.Render(gpu, self.Film)
+        dt = time.perf_counter() - t0
+        print(f"Render time: {dt:f} seconds")
+        if filename:
+            self.Film.Save(filename)
+        return dt
+
+    def close(self):
+        if self._gpu is not None:
+            self._gpu.close()
+            self._gpu = None
+        if self._h:
+            self._lib.bn_host_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close

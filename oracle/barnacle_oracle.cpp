@@ -1,0 +1,1003 @@
+// barnacle_oracle.cpp — ORACLE (test infrastructure, NOT product code).
+//
+// CPU restatement of Barnacle's path-tracing hot path, following the F# sources
+// under /root/reference line by line (citations `File.fs:lines` on every
+// function).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+// / --impl reference legs may build, load or call this file; the product
+// (barnacle_b200/) never does.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+//  and its .NET 9 toolchain is absent from this image, so this
+// restatement cannot be checked against outputs of the reference itself.  It is
+// pinned instead by (1) integer known-answer vectors derived from Util/Hash.fs,
+// (2) analytically known micro-scenes, (3) structural invariants of the BVH
+// builder, (4) an independent numpy restatement of the builder
+// (oracle/bvh_build_np.py).  Every "matches the reference" claim made with it
+// reads "matches the C++ restatement of the reference".
+//
+// Third-party arithmetic not under /root/reference: .NET 9 BCL
+// (System.Numerics.Vector3/Matrix4x4, MathF/Math), pinned only as `net9.0`
+// (Barnacle.fsproj:5).  Conventions assumed, switchable by
+// BN_NET9_FMA: Vector3.Cross and Vector3.Transform use fused multiply-add
+// chains, Dot is ((x*x' + y*y') + z*z'), MinNative/MaxNative are minps/maxps,
+// Math.Max/Min propagate NaN, MathF.ReciprocalEstimate is restated as IEEE 1/x
+// (SURVEY Q11 — not bit-reproducible even CPU to CPU).
+//
+// Build: g++ -O2 -ffp-contract=off -mavx2 -mfma -fopenmp (see oracle/Makefile).
+// -ffp-contract=off is REQUIRED: every fused op below is an explicit fmaf.
+#include <omp.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../include/barnacle_b200.h"   // POD layouts of the boundary only
+#include "../include/bn_portable_math.h"
+
+#ifndef BN_NET9_FMA
+#define BN_NET9_FMA 1
+#endif
+
+namespace {
+
+// ----------------------------------------------------------------------------
+// math mode: 0 = platform libm (what the reference does), 1 = bit-reproducible
+// definitions of include/bn_portable_math.h (what the CUDA kernels evaluate)
+// ----------------------------------------------------------------------------
+int g_portable_math = 1;
+
+inline void o_sincos(float x, float& s, float& c) {
+  if (g_portable_math) bn_sincosf(x, &s, &c);
+  else { s = sinf(x); c = cosf(x); }
+}
+inline float o_atan(float x) { return g_portable_math ? bn_atanf(x) : atanf(x); }
+
+constexpr float kPi = 3.14159274101257324f;  // MathF.PI
+constexpr float kInf = std::numeric_limits<float>::infinity();
+constexpr float kSingleEpsilon = 1.401298464324817e-45f;  // Single.Epsilon (smallest denormal)
+
+struct V2 { float x, y; };
+struct V3 {
+  float x, y, z;
+  float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, V3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+inline V3 splat(float s) { return {s, s, s}; }
+inline V3 vfma(V3 a, V3 b, V3 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z)}; }  // Vector3.FusedMultiplyAdd
+inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline float length_sq(V3 a) { return dot(a, a); }
+inline float length(V3 a) { return sqrtf(dot(a, a)); }
+inline V3 normalize(V3 a) { return a / length(a); }
+inline V3 cross(V3 a, V3 b) {
+#if BN_NET9_FMA
+  return {fmaf(-a.z, b.y, a.y * b.z), fmaf(-a.x, b.z, a.z * b.x), fmaf(-a.y, b.x, a.x * b.y)};
+#else
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+#endif
+}
+inline V3 min_native(V3 a, V3 b) { return {a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z < b.z ? a.z : b.z}; }
+inline V3 max_native(V3 a, V3 b) { return {a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y, a.z > b.z ? a.z : b.z}; }
+// Math.Max / Math.Min (float): IEEE 754-2019 maximum/minimum, NaN-propagating
+inline float net_max(float a, float b) {
+  if (a != b) { if (!std::isnan(a)) return b < a ? a : b; return a; }
+  return std::signbit(b) ? a : b;
+}
+inline float net_min(float a, float b) {
+  if (a != b) { if (!std::isnan(a)) return a < b ? a : b; return a; }
+  return std::signbit(a) ? a : b;
+}
+inline V3 load3(const float* p) { return {p[0], p[1], p[2]}; }
+
+// Vector3.Transform(position, M) — row-vector convention
+inline V3 transform_point(V3 p, const float* M) {
+  float r[3];
+  for (int j = 0; j < 3; ++j) {
+#if BN_NET9_FMA
+    float v = M[j] * p.x;
+    v = fmaf(M[4 + j], p.y, v);
+    v = fmaf(M[8 + j], p.z, v);
+    r[j] = v + M[12 + j];
+#else
+    r[j] = ((p.x * M[j] + p.y * M[4 + j]) + p.z * M[8 + j]) + M[12 + j];
+#endif
+  }
+  return {r[0], r[1], r[2]};
+}
+inline V3 translation(const float* M) { return {M[12], M[13], M[14]}; }
+// "Transform(dir, M) - M.Translation" 
+inline V3 transform_dir(V3 d, const float* M) { return transform_point(d, M) - translation(M); }
+
+// ---- Base/Ray.fs ------------------------------------------------------------
+struct Ray {
+  V3 o, d;
+  V3 point_at(float t) const { return vfma(splat(t), d, o); }  // Ray.fs:16-17
+};
+inline Ray transform_ray(const Ray& r, const float* M) {       // Ray.fs:19-22
+  return {transform_point(r.o, M), transform_dir(r.d, M)};
+}
+// AxisAlignedBoundingBox.Intersect — Ray.fs:29-39
+inline bool aabb_intersect(V3 pmin, V3 pmax, const Ray& ray, float t) {
+  V3 inv{1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z};
+  float tmin = 1e-3f, tmax = t;
+  V3 t0 = (pmin - ray.o) * inv;
+  V3 t1 = (pmax - ray.o) * inv;
+  V3 lo = min_native(t0, t1);
+  V3 hi = max_native(t0, t1);
+  tmin = net_max(tmin, net_max(lo.x, net_max(lo.y, lo.z)));
+  tmax = net_min(tmax, net_min(hi.x, net_min(hi.y, hi.z)));
+  return tmin <= tmax;
+}
+
+// ---- Base/Primitive.fs ------------------------------------------------------
+struct Onb { V3 n, t, b; };
+inline Onb onb_from_n(V3 n) {  // Primitive.fs:15-23
+  V3 axis = fabsf(n.x) > 0.1f ? V3{0, 1, 0} : V3{1, 0, 0};
+  V3 t = normalize(cross(n, axis));
+  return {n, t, cross(n, t)};
+}
+inline V3 local_to_world(const Onb& f, V3 v) { return (v.x * f.t + v.y * f.b) + v.z * f.n; }       // :28-29
+inline V3 world_to_local(const Onb& f, V3 v) { return {dot(v, f.t), dot(v, f.b), dot(v, f.n)}; }   // :31-32
+inline Onb transform_onb(const Onb& f, const float* M) {  // :34-38 (n' not renormalised)
+  V3 t = normalize(transform_dir(f.t, M));
+  V3 b = normalize(transform_dir(f.b, M));
+  return {cross(t, b), t, b};
+}
+struct Geom {  // LocalGeometry, :42-60
+  V3 p;
+  Onb onb;
+  V2 uv;
+  int tag;   // reset to 0 by LocalGeometry.Transform
+  int prim;  // ORACLE-ONLY: BLAS-order triangle id before that reset (hit-parity export)
+};
+struct Interaction {
+  Geom geom;
+  int inst;  // TLAS-order instance index
+};
+
+// ---- scene ------------------------------------------------------------------
+struct Counters {
+  uint64_t tlas_nodes = 0, blas_nodes = 0, tris_fetched = 0, tris_box_pass = 0;
+  uint64_t inst_visited = 0, inst_box_pass = 0, inst_committed = 0, rays = 0;
+  void add(const Counters& o) {
+    tlas_nodes += o.tlas_nodes; blas_nodes += o.blas_nodes; tris_fetched += o.tris_fetched;
+    tris_box_pass += o.tris_box_pass; inst_visited += o.inst_visited; inst_box_pass += o.inst_box_pass;
+    inst_committed += o.inst_committed; rays += o.rays;
+  }
+};
+
+struct Scene {
+  std::vector<BnBVHNode> tlas, blas;
+  std::vector<BnInstance> inst;
+  std::vector<uint32_t> light_inst;
+  std::vector<BnMesh> meshes;
+  std::vector<float> verts;
+  std::vector<int32_t> tris;
+  std::vector<BnAliasEntry> alias;
+  std::vector<float> radii;
+  std::vector<BnMaterial> mats;
+  std::vector<BnLight> lights;
+  BnCamera cam;
+};
+
+struct Tri { V3 p0, p1, p2; };
+inline Tri mesh_tri(const Scene& s, const BnMesh& m, int i) {  // MeshPrimitive.Item, Mesh.fs:174-179
+  const int32_t* ix = &s.tris[(size_t)(m.tri_offset + i) * 3];
+  const float* v = &s.verts[(size_t)m.vertex_offset * 3];
+  return {load3(v + ix[0] * 3), load3(v + ix[1] * 3), load3(v + ix[2] * 3)};
+}
+inline void tri_bounds(const Tri& t, V3& lo, V3& hi) {  // Triangle.Bounds, Mesh.fs:19-22
+  lo = min_native(min_native(t.p0, t.p1), t.p2);
+  hi = max_native(max_native(t.p0, t.p1), t.p2);
+}
+
+// Triangle.Intersect/2 — Mesh.fs:24-48
+inline bool tri_any(const Tri& tr, const Ray& ray, float t) {
+  V3 e0 = tr.p1 - tr.p0, e1 = tr.p2 - tr.p0;
+  V3 rce1 = cross(ray.d, e1);
+  float det = dot(e0, rce1);
+  if (fabsf(det) < kSingleEpsilon) return false;
+  float inv = 1.f / det;
+  V3 s = ray.o - tr.p0;
+  float u = inv * dot(s, rce1);
+  if (u < 0.f || u > 1.f) return false;
+  V3 sce0 = cross(s, e0);
+  float v = inv * dot(ray.d, sce0);
+  if (v < 0.f || u + v > 1.f) return false;
+  float tp = inv * dot(e1, sce0);
+  return tp > kSingleEpsilon && tp < t;
+}
+// Triangle.Intersect/3 — Mesh.fs:50-82
+inline bool tri_closest(const Tri& tr, const Ray& ray, Geom& geom, float& t) {
+  V3 e0 = tr.p1 - tr.p0, e1 = tr.p2 - tr.p0;
+  V3 rce1 = cross(ray.d, e1);
+  float det = dot(e0, rce1);
+  if (fabsf(det) < kSingleEpsilon) return false;
+  float inv = 1.f / det;
+  V3 s = ray.o - tr.p0;
+  float u = inv * dot(s, rce1);
+  if (u < 0.f || u > 1.f) return false;
+  V3 sce0 = cross(s, e0);
+  float v = inv * dot(ray.d, sce0);
+  if (v < 0.f || u + v > 1.f) return false;
+  float tp = inv * dot(e1, sce0);
+  if (tp > kSingleEpsilon && tp < t) {
+    V3 n = normalize(cross(e0, e1));
+    geom.p = ray.point_at(tp);
+    geom.onb = onb_from_n(n);
+    geom.uv = {u, v};
+    geom.tag = 0;
+    t = tp;
+    return true;
+  }
+  return false;
+}
+
+// MeshPrimitive.Intersect/3 (BLAS closest hit) — Mesh.fs:217-242
+template <bool COUNT>
+bool mesh_closest(const Scene& s, const BnMesh& m, const Ray& ray, Geom& geom, float& t, Counters* c) {
+  const BnBVHNode* nodes = &s.blas[m.node_offset];
+  int stack[128];
+  int top = 0;
+  stack[top++] = 0;
+  bool hit = false;
+  while (top != 0) {
+    int i = stack[--top];
+    const BnBVHNode& node = nodes[i];
+    if (COUNT) c->blas_nodes++;
+    if (aabb_intersect(load3(node.bounds_min), load3(node.bounds_max), ray, t)) {
+      if (node.is_leaf) {
+        for (int id = node.right_or_offset; id <= node.right_or_offset + node.count - 1; ++id) {
+          Tri tr = mesh_tri(s, m, id);
+          if (COUNT) c->tris_fetched++;
+          V3 lo, hi;
+          tri_bounds(tr, lo, hi);
+          if (aabb_intersect(lo, hi, ray, t)) {
+            if (COUNT) c->tris_box_pass++;
+            if (tri_closest(tr, ray, geom, t)) {
+              geom.tag = id;
+              geom.prim = id;
+              hit = true;
+            }
+          }
+        }
+      } else if (ray.d[node.split_axis] > 0.f) {
+        stack[top++] = node.right_or_offset;
+        stack[top++] = i + 1;
+      } else {
+        stack[top++] = i + 1;
+        stack[top++] = node.right_or_offset;
+      }
+    }
+  }
+  return hit;
+}
+
+// MeshPrimitive.Intersect/2 (BLAS any hit) — Mesh.fs:188-215.  stackTop starts
+// at 1 and slot 0 is read as zero-initialised memory, so the root is walked a
+// second time when the first pass finds nothing — kept, it is what
+// the reference's CPU time contains.
+template <bool COUNT>
+bool mesh_any(const Scene& s, const BnMesh& m, const Ray& ray, float t, Counters* c) {
+  const BnBVHNode* nodes = &s.blas[m.node_offset];
+  int stack[66];
+  stack[0] = 0;
+  int top = 1;
+  stack[top++] = 0;
+  bool hit = false;
+  while (!hit && top != 0) {
+    int i = stack[--top];
+    const BnBVHNode& node = nodes[i];
+    if (COUNT) c->blas_nodes++;
+    if (aabb_intersect(load3(node.bounds_min), load3(node.bounds_max), ray, t)) {
+      if (node.is_leaf) {
+        int id = node.right_or_offset;
+        while (!hit && id < node.right_or_offset + node.count) {
+          Tri tr = mesh_tri(s, m, id);
+          if (COUNT) c->tris_fetched++;
+          V3 lo, hi;
+          tri_bounds(tr, lo, hi);
+          if (aabb_intersect(lo, hi, ray, t)) {
+            if (COUNT) c->tris_box_pass++;
+            hit = tri_any(tr, ray, t);
+          }
+          ++id;
+        }
+      } else if (ray.d[node.split_axis] > 0.f) {
+        stack[top++] = node.right_or_offset;
+        stack[top++] = i + 1;
+      } else {
+        stack[top++] = i + 1;
+        stack[top++] = node.right_or_offset;
+      }
+    }
+  }
+  return hit;
+}
+
+// SpherePrimitive.Intersect/2 — Sphere.fs:13-33
+inline bool sphere_any(float radius, const Ray& ray, float t) {
+  const float eps = 1e-3f;
+  V3 f = ray.o;
+  float a = length_sq(ray.d);
+  float b = -dot(f, ray.d);
+  float r2 = radius * radius;
+  float c = length_sq(f) - r2;
+  float d = r2 - length_sq(f + (b / a) * ray.d);
+  if (d < 0.f) return false;
+  float q = b + copysignf(sqrtf(a * d), b);
+  float t0 = c / q;
+  if (t0 > eps && t0 < t) return true;
+  float t1 = q / a;
+  return t1 > eps && t1 < t;
+}
+inline V2 sphere_uv(V3 n) {  // Sphere.fs:55-56 (libm atan2/acos; uv is unused by every material/light)
+  return {atan2f(n.z, n.x) / (2.f * kPi) + 0.5f, acosf(n.y) / kPi};
+}
+// SpherePrimitive.Intersect/3 — Sphere.fs:35-77 (far root keeps the outward normal)
+inline bool sphere_closest(float radius, const Ray& ray, Geom& geom, float& t) {
+  const float eps = 1e-3f;
+  V3 f = ray.o;
+  float a = length_sq(ray.d);
+  float b = -dot(f, ray.d);
+  float r2 = radius * radius;
+  float c = length_sq(f) - r2;
+  float d = r2 - length_sq(f + (b / a) * ray.d);
+  if (d < 0.f) return false;
+  float q = b + copysignf(sqrtf(a * d), b);
+  float t0 = c / q;
+  if (t0 > eps && t0 < t) {
+    t = t0;
+    V3 p = ray.point_at(t);
+    V3 n = normalize(p);
+    V2 uv = sphere_uv(n);
+    if (dot(n, ray.d) > 0.f) n = -n;
+    geom.p = p; geom.onb = onb_from_n(n); geom.uv = uv; geom.tag = 0; geom.prim = 0;
+    return true;
+  }
+  float t1 = q / a;
+  if (t1 > eps && t1 < t) {
+    t = t1;
+    V3 p = ray.point_at(t);
+    V3 n = normalize(p);
+    geom.p = p; geom.onb = onb_from_n(n); geom.uv = sphere_uv(n); geom.tag = 0; geom.prim = 0;
+    return true;
+  }
+  return false;
+}
+
+// PrimitiveInstance.Intersect/3 — Primitive.fs:118-129
+template <bool COUNT>
+bool instance_closest(const Scene& s, int id, const Ray& ray, Interaction& it, float& t, Counters* c) {
+  const BnInstance& in = s.inst[id];
+  if (COUNT) c->inst_visited++;
+  if (!aabb_intersect(load3(in.bounds_min), load3(in.bounds_max), ray, t)) return false;
+  if (COUNT) c->inst_box_pass++;
+  Ray ro = transform_ray(ray, in.world_to_object);
+  bool hit = in.prim_kind == BN_PRIM_MESH ? mesh_closest<COUNT>(s, s.meshes[in.prim_id], ro, it.geom, t, c)
+                                          : sphere_closest(s.radii[in.prim_id], ro, it.geom, t);
+  if (!hit) return false;
+  if (COUNT) c->inst_committed++;
+  // LocalGeometry.Transform — Primitive.fs:57-58 (tag -> 0)
+  it.geom.p = transform_point(it.geom.p, in.object_to_world);
+  it.geom.onb = transform_onb(it.geom.onb, in.object_to_world);
+  it.geom.tag = 0;
+  it.inst = id;
+  return true;
+}
+// PrimitiveInstance.Intersect/2 — Primitive.fs:111-116
+template <bool COUNT>
+bool instance_any(const Scene& s, int id, const Ray& ray, float t, Counters* c) {
+  const BnInstance& in = s.inst[id];
+  if (COUNT) c->inst_visited++;
+  if (!aabb_intersect(load3(in.bounds_min), load3(in.bounds_max), ray, t)) return false;
+  if (COUNT) c->inst_box_pass++;
+  Ray ro = transform_ray(ray, in.world_to_object);
+  return in.prim_kind == BN_PRIM_MESH ? mesh_any<COUNT>(s, s.meshes[in.prim_id], ro, t, c)
+                                      : sphere_any(s.radii[in.prim_id], ro, t);
+}
+
+// BVHAggregate.Intersect/3 (TLAS closest) — Aggregate/BVH.fs:37-58
+template <bool COUNT>
+bool scene_closest(const Scene& s, const Ray& ray, Interaction& it, float& t, Counters* c) {
+  int stack[65];
+  int top = 0;
+  stack[top++] = 0;
+  bool hit = false;
+  if (COUNT) c->rays++;
+  while (top != 0) {
+    int i = stack[--top];
+    const BnBVHNode& node = s.tlas[i];
+    if (COUNT) c->tlas_nodes++;
+    if (aabb_intersect(load3(node.bounds_min), load3(node.bounds_max), ray, t)) {
+      if (node.is_leaf) {
+        for (int id = node.right_or_offset; id <= node.right_or_offset + node.count - 1; ++id)
+          hit = instance_closest<COUNT>(s, id, ray, it, t, c) || hit;
+      } else if (ray.d[node.split_axis] > 0.f) {
+        stack[top++] = node.right_or_offset;
+        stack[top++] = i + 1;
+      } else {
+        stack[top++] = i + 1;
+        stack[top++] = node.right_or_offset;
+      }
+    }
+  }
+  return hit;
+}
+// BVHAggregate.Intersect/2 (TLAS any) — Aggregate/BVH.fs:11-35
+template <bool COUNT>
+bool scene_any(const Scene& s, const Ray& ray, float t, Counters* c) {
+  int stack[128];
+  int top = 0;
+  stack[top++] = 0;
+  bool hit = false;
+  if (COUNT) c->rays++;
+  while (!hit && top != 0) {
+    int i = stack[--top];
+    const BnBVHNode& node = s.tlas[i];
+    if (COUNT) c->tlas_nodes++;
+    if (aabb_intersect(load3(node.bounds_min), load3(node.bounds_max), ray, t)) {
+      if (node.is_leaf) {
+        int id = node.right_or_offset;
+        while (!hit && id < node.right_or_offset + node.count) {
+          hit = instance_any<COUNT>(s, id, ray, t, c);
+          ++id;
+        }
+      } else if (ray.d[node.split_axis] > 0.f) {
+        stack[top++] = node.right_or_offset;
+        stack[top++] = i + 1;
+      } else {
+        stack[top++] = i + 1;
+        stack[top++] = node.right_or_offset;
+      }
+    }
+  }
+  return hit;
+}
+
+// ---- Util/Hash.fs, Base/Sampler.fs -------------------------------------------
+inline uint32_t rotl17(uint32_t h) { return (h << 17) | (h >> 15); }
+inline uint32_t xxhash32_two(uint32_t x, uint32_t y) {  // Hash.fs:6-15
+  const uint32_t p2 = 2246822519u, p3 = 3266489917u, p4 = 668265263u, p5 = 374761393u;
+  uint32_t h = y + p5 + x * p3;
+  h = p4 * rotl17(h);
+  h = p2 * (h ^ (h >> 15));
+  h = p3 * (h ^ (h >> 13));
+  return h ^ (h >> 16);
+}
+inline uint32_t xxhash32_three(uint32_t x, uint32_t y, uint32_t z) {  // Hash.fs:17-28
+  const uint32_t p2 = 2246822519u, p3 = 3266489917u, p4 = 668265263u, p5 = 374761393u;
+  uint32_t h = z + p5 + x * p3;
+  h = p4 * rotl17(h);
+  h = h + y * p3;
+  h = p4 * rotl17(h);
+  h = p2 * (h ^ (h >> 15));
+  h = p3 * (h ^ (h >> 13));
+  return h ^ (h >> 16);
+}
+inline float lcg(uint32_t& seed) {  // Hash.fs:30-32
+  seed = 0x00269ec3u + seed * 0x000343fdu;
+  uint32_t bits = (seed >> 9) | 0x3f800000u;
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f - 1.f;
+}
+struct Sampler {  // Sampler.fs:7-16
+  uint32_t state;
+  float next1d() { return lcg(state); }
+  V2 next2d() { float a = next1d(); float b = next1d(); return {a, b}; }
+};
+
+// ---- cameras ------------------------------------------------------------------
+// PinholeCamera.GenerateRay — Pinhole.fs:12-27
+inline Ray pinhole_ray(const BnCamera& cam, int w, int h, int x, int y, V2 up) {
+  float vh = 2.f * tanf(cam.fov_y * kPi / 360.f);
+  float vw = vh * cam.aspect_ratio;
+  V3 vu = vw * V3{1, 0, 0}, vv = vh * V3{0, 1, 0};
+  V3 du = vu / (float)w, dv = vv / (float)h;
+  V3 ul = -V3{0, 0, 1} - 0.5f * (vu + vv);
+  V3 loc = (ul + ((float)x + up.x) * du) + ((float)y + up.y) * dv;
+  return {{0, 0, 0}, normalize(loc)};
+}
+// ThinLensCamera.SampleDiskConcentric — ThinLens.fs:12-23
+inline V2 sample_disk_concentric(V2 ul) {
+  V2 u{ul.x * 2.f - 1.f, ul.y * 2.f - 1.f};
+  if (u.x == 0.f || u.y == 0.f) return {0, 0};
+  float r, theta;
+  if (fabsf(u.x) > fabsf(u.y)) { r = u.x; theta = kPi / 4.f * (u.y / u.x); }
+  else { r = u.y; theta = kPi / 2.f - kPi / 4.f * (u.x / u.y); }
+  float s, c;
+  o_sincos(theta, s, c);
+  return {r * c, r * s};
+}
+// CameraBase.GeneratePrimaryRay — Camera.fs:12-20 (+ ThinLens.fs:25-35)
+inline Ray primary_ray(const BnCamera& cam, int w, int h, int x, int y, V2 up, V2 ul) {
+  Ray ray = pinhole_ray(cam, w, h, x, y, up);
+  if (cam.type == BN_CAM_THIN_LENS && cam.aperture > 0.f) {
+    V2 d = sample_disk_concentric(ul);
+    V2 pl{cam.aperture * d.x, cam.aperture * d.y};
+    V3 origin = ray.o + V3{pl.x, pl.y, 0.f};
+    V3 dir = normalize(ray.point_at(cam.focus_distance) - origin);
+    ray = {origin, dir};
+  }
+  ray.o = transform_point(ray.o, cam.camera_to_world);
+  ray.d = normalize(transform_dir(ray.d, cam.camera_to_world));
+  ray.o = ray.point_at(cam.push_forward);
+  return ray;
+}
+
+// ---- materials ------------------------------------------------------------------
+struct BSDFEval { V3 bsdf; float pdf; };
+struct BSDFSample { BSDFEval eval; V3 wi; };
+
+// Lambertian.Eval — Lambertian.fs:11-16
+inline BSDFEval lambert_eval(const BnMaterial& m, V3 wo, V3 wi) {
+  if (wi.z * wo.z < 0.f || net_min(fabsf(wi.z), fabsf(wo.z)) < 1e-6f) return {{0, 0, 0}, 0.f};
+  float pdf = fabsf(wi.z) / kPi;
+  return {load3(m.base_color) * pdf, pdf};
+}
+inline V3 cosine_hemisphere(V2 u) {  // Lambertian.fs:19-22, PBR.fs:60-63
+  float ct = sqrtf(u.x), st = sqrtf(1.f - u.x);
+  float sp, cp;
+  o_sincos(2.f * kPi * u.y, sp, cp);
+  return {st * cp, st * sp, ct};
+}
+// Lambertian.Sample — Lambertian.fs:18-26
+inline BSDFSample lambert_sample(const BnMaterial& m, V3 wo, V2 u) {
+  V3 wi = cosine_hemisphere(u);
+  float pdf = wi.z / kPi;
+  return {{load3(m.base_color) * pdf, pdf}, wo.z > 0.f ? wi : -wi};
+}
+// DielectricMaterial.Sample — Dielectric.fs:15-31
+inline BSDFSample dielectric_sample(const BnMaterial& m, V3 wo, float ulobe) {
+  V3 base = load3(m.base_color);
+  float ior = m.p0;
+  float iorp = wo.z > 0.f ? 1.f / ior : ior;
+  float cos2 = 1.f - iorp * iorp * fmaf(-wo.z, wo.z, 1.f);
+  if (cos2 <= 0.f) return {{base, 1.f}, {-wo.x, -wo.y, wo.z}};
+  float a = iorp - 1.f, b = iorp + 1.f;
+  float r0 = a * a / (b * b);
+  float c = 1.f - fabsf(wo.z);
+  float c2 = c * c;
+  float r = r0 + (1.f - r0) * c2 * c2 * c;
+  if (ulobe < r) return {{r * base, r}, {-wo.x, -wo.y, wo.z}};
+  float ct = sqrtf(cos2);
+  return {{(1.f - r) * base, 1.f - r}, {-wo.x * iorp, -wo.y * iorp, -copysignf(ct, wo.z)}};
+}
+// PBRMaterial — PBR.fs:13-64 (no validity checks, NaN possible)
+inline float pbr_lambda(float alpha, V3 w) {
+  float sin2 = fmaf(w.x, w.x, w.y * w.y);
+  if (sin2 == 0.f) return 0.f;
+  float tan2 = sin2 / (w.z * w.z);
+  float a2t2 = alpha * alpha * tan2;
+  return (-1.f + sqrtf(1.f + a2t2)) / 2.f;
+}
+inline float pbr_d(float alpha, V3 wh) {
+  float ch = fabsf(wh.z);
+  float x = 1.f + fmaf(alpha, alpha, -1.f) * ch * ch;
+  return alpha * alpha / (kPi * (x * x));
+}
+inline BSDFEval pbr_eval(const BnMaterial& m, V3 wo, V3 wi) {
+  V3 base = load3(m.base_color);
+  float metallic = m.p0, alpha = m.p1;
+  V3 wh = normalize(wo + wi);
+  float d = pbr_d(alpha, wh);
+  float g = 1.f / (1.f + pbr_lambda(alpha, wo) + pbr_lambda(alpha, wi));
+  float spec = d * g / (4.f * fabsf(wo.z));
+  float ct = dot(wo, wh);
+  float c = 1.f - ct;
+  float c2 = c * c;
+  V3 fc = base + (splat(1.f) - base) * (c2 * c2 * c);   // ConductorFresnel :26-30
+  V3 metal = spec * fc;
+  float f0 = 0.04f;
+  float f = f0 + (1.f - f0) * c2 * c2 * c;             // DielectricFresnel :31-36
+  V3 diffuse = base * fabsf(wi.z) / kPi;
+  auto mixv = [](V3 a, V3 b, float t) { return vfma(a, splat(1.f - t), b * t); };
+  V3 bsdf = mixv(mixv(diffuse, splat(spec), f), metal, metallic);
+  float t = 0.5f * (1.f - metallic);
+  float pdf = fmaf(d * fabsf(wh.z) / (4.f * dot(wo, wh)), 1.f - t, (fabsf(wi.z) / kPi) * t);
+  return {bsdf, pdf};
+}
+inline BSDFSample pbr_sample(const BnMaterial& m, V3 wo, float ulobe, V2 u) {
+  float metallic = m.p0, alpha = m.p1;
+  V3 wi;
+  if (ulobe < 1.f - 0.5f * (1.f - metallic)) {
+    float th = o_atan(alpha * sqrtf(u.x / (1.f - u.x)));
+    float ph = 2.f * kPi * u.y;
+    float st, ct, sp, cp;
+    o_sincos(th, st, ct);
+    o_sincos(ph, sp, cp);
+    V3 wh{st * cp, st * sp, ct};
+    wi = 2.f * dot(wo, wh) * wh - wo;
+  } else {
+    wi = cosine_hemisphere(u);
+  }
+  return {pbr_eval(m, wo, wi), wi};
+}
+inline BSDFEval material_eval(const BnMaterial& m, V3 wo, V3 wi) {
+  switch (m.type) {
+    case BN_MAT_LAMBERTIAN: return lambert_eval(m, wo, wi);
+    case BN_MAT_PBR: return pbr_eval(m, wo, wi);
+    default: return {{0, 0, 0}, 0.f};  // Mirror.fs:11, Dielectric.fs:13-14
+  }
+}
+inline BSDFSample material_sample(const BnMaterial& m, V3 wo, float ulobe, V2 u) {
+  switch (m.type) {
+    case BN_MAT_LAMBERTIAN: return lambert_sample(m, wo, u);
+    case BN_MAT_MIRROR: return {{load3(m.base_color), 1.f}, {-wo.x, -wo.y, wo.z}};  // Mirror.fs:12-14
+    case BN_MAT_DIELECTRIC: return dielectric_sample(m, wo, ulobe);
+    default: return pbr_sample(m, wo, ulobe, u);
+  }
+}
+
+// ---- lights -----------------------------------------------------------------------
+// DiffuseLight.Eval — Light.fs:49-53 (wo in the local frame; only wo.z matters)
+inline V3 light_eval(const BnLight& l, float woz) {
+  if (fabsf(woz) > 1e-6f && (woz > 0.f || l.two_sided)) return load3(l.emission);
+  return {0, 0, 0};
+}
+inline float tri_area(const Tri& t) { return 0.5f * length(cross(t.p1 - t.p0, t.p2 - t.p0)); }  // Mesh.fs:84-87
+inline Tri transform_tri(const Tri& t, const float* M) {  // Mesh.fs:101-111
+  return {transform_point(t.p0, M), transform_point(t.p1, M), transform_point(t.p2, M)};
+}
+// AliasTable.Sample — AliasTable.fs:52-62
+inline int alias_sample(const BnAliasEntry* table, int n, float u, float& pdf) {
+  u = u * (float)n;
+  int idx = (int)u;
+  const BnAliasEntry& e = table[idx];
+  u = u - (float)idx;
+  if (u < e.prob) { pdf = e.pdf; return idx; }
+  pdf = table[e.alias].pdf;
+  return e.alias;
+}
+// MeshInstance.Sample — Mesh.fs:289-298 (+ Triangle.Sample :89-99)
+inline float mesh_instance_sample(const Scene& s, const BnInstance& in, float usel, V2 us, V3& p, V3& n) {
+  const BnMesh& m = s.meshes[in.prim_id];
+  float pdf_tri;
+  int i = alias_sample(&s.alias[m.alias_offset], (int)m.tri_count, usel, pdf_tri);
+  Tri t = transform_tri(mesh_tri(s, m, i), in.object_to_world);
+  V2 uv = us.x < us.y ? V2{0.5f * us.x, fmaf(-0.5f, us.x, us.y)} : V2{fmaf(-0.5f, us.y, us.x), 0.5f * us.y};
+  p = (uv.x * t.p1 + uv.y * t.p2) + (1.f - uv.x - uv.y) * t.p0;
+  V3 nn = cross(t.p1 - t.p0, t.p2 - t.p0);
+  float pdf = 2.f / length(nn);
+  n = (0.5f * pdf) * nn;
+  return pdf_tri * pdf;
+}
+// MeshInstance.EvalPDF — Mesh.fs:300-304 (tag is always 0 here)
+inline float mesh_instance_pdf(const Scene& s, const BnInstance& in, int tag) {
+  const BnMesh& m = s.meshes[in.prim_id];
+  Tri t = transform_tri(mesh_tri(s, m, tag), in.object_to_world);
+  return s.alias[m.alias_offset + tag].pdf / tri_area(t);
+}
+// SphereInstance.Sample — Sphere.fs:90-113
+inline float sphere_instance_sample(const Scene& s, const BnInstance& in, V2 us, V3& p, V3& n) {
+  float radius = s.radii[in.prim_id];
+  float st, ct;
+  o_sincos(2.f * kPi * us.x, st, ct);
+  float cphi = fmaf(-2.f, us.y, 1.f);
+  float sphi = sqrtf(fmaf(-cphi, cphi, 1.f));
+  V3 nl{ct * sphi, st * sphi, cphi};
+  Onb f = onb_from_n(nl);
+  V3 pp = transform_point(nl * radius, in.object_to_world);
+  V3 tp = transform_dir(f.t, in.object_to_world);
+  V3 bp = transform_dir(f.b, in.object_to_world);
+  V3 np = cross(tp, bp);
+  float inv_j = 1.f / length(np);
+  p = pp;
+  n = inv_j * np;
+  return inv_j / (4.f * kPi * radius * radius);
+}
+// SphereInstance.EvalPDF — Sphere.fs:115-126
+inline float sphere_instance_pdf(const Scene& s, const BnInstance& in, const Onb& f) {
+  float radius = s.radii[in.prim_id];
+  V3 tp = transform_dir(f.t, in.world_to_object);
+  V3 bp = transform_dir(f.b, in.world_to_object);
+  float j = length(cross(tp, bp));
+  return j / (4.f * kPi * radius * radius);
+}
+
+struct LightEval { V3 p, L; float pdf; };
+struct LightSample { LightEval eval; V3 wi; };
+
+// UniformLightSampler.Sample — Uniform.fs:13-29
+inline LightSample light_sampler_sample(const Scene& s, V3 p, float usel, V2 ul) {
+  int n = (int)s.light_inst.size();
+  usel = usel * (float)n;
+  int id = std::min((int)usel, n - 1);
+  usel = usel - (float)id;
+  const BnInstance& in = s.inst[s.light_inst[id]];
+  V3 ip, inorm;
+  float pdf_surface = in.prim_kind == BN_PRIM_MESH ? mesh_instance_sample(s, in, usel, ul, ip, inorm)
+                                                   : sphere_instance_sample(s, in, ul, ip, inorm);
+  V3 wo = normalize(p - ip);
+  float cos_wo = dot(inorm, wo);
+  float dist2 = length_sq(p - ip);
+  // EvalEmit(wo) = Light.Eval(onb.WorldToLocal(wo)) — only z = dot(wo, n) is used
+  V3 L = light_eval(s.lights[in.light_id], dot(wo, inorm));
+  float pdf = dist2 * pdf_surface / (net_max(fabsf(cos_wo), 1e-6f) * (float)n);
+  return {{ip, L, pdf}, -wo};
+}
+// UniformLightSampler.Eval — Uniform.fs:40-49
+inline LightEval light_sampler_eval(const Scene& s, V3 p, const Interaction& it) {
+  int n = (int)s.light_inst.size();
+  const BnInstance& in = s.inst[it.inst];
+  V3 wo = normalize(p - it.geom.p);
+  float cos_wo = dot(it.geom.onb.n, wo);
+  float pdf_surface = in.prim_kind == BN_PRIM_MESH ? mesh_instance_pdf(s, in, it.geom.tag)
+                                                   : sphere_instance_pdf(s, in, it.geom.onb);
+  float dist2 = length_sq(p - it.geom.p);
+  V3 L = light_eval(s.lights[in.light_id], dot(wo, it.geom.onb.n));
+  return {it.geom.p, L, dist2 * pdf_surface / (net_max(fabsf(cos_wo), 1e-6f) * (float)n)};
+}
+
+// ---- PathTracingIntegrator.Li — PathTracing.fs:14-81 ---------------------------------
+struct PathStats { uint64_t extend = 0, shadow = 0, shadow_nonnull = 0; };
+
+template <bool COUNT>
+V3 path_li(const Scene& s, Ray ray, Sampler& sampler, int max_depth, int rr_depth, PathStats& ps, Counters* ce, Counters* cs) {
+  V3 L{0, 0, 0}, beta{1, 1, 1};
+  int depth = 0;
+  Interaction it{};
+  float prev_bsdf_pdf = 0.f;
+  while (depth < max_depth) {
+    float t = kInf;
+    ps.extend++;
+    if (!scene_closest<COUNT>(s, ray, it, t, ce)) { depth = max_depth; continue; }
+    const BnInstance& in = s.inst[it.inst];
+    if (in.light_id >= 0) {  // :30-40
+      LightEval le = light_sampler_eval(s, ray.o, it);
+      float w = depth == 0 ? 1.f : prev_bsdf_pdf * (1.f / (le.pdf + prev_bsdf_pdf));
+      L = vfma(beta, le.L * w, L);
+    }
+    if (in.material_id < 0) { depth = max_depth; continue; }  // :78-79
+    const BnMaterial& mat = s.mats[in.material_id];
+    float usel = sampler.next1d();
+    V2 ul = sampler.next2d();
+    LightSample ls = light_sampler_sample(s, it.geom.p, usel, ul);  // :43
+    Ray shadow{it.geom.p, ls.wi};
+    float dist = length(ls.eval.p - it.geom.p);
+    V3 wo_l = world_to_local(it.geom.onb, -ray.d);
+    if (ls.eval.pdf != 0.f) {  // :47-59
+      ps.shadow++;
+      if (COUNT) {  // instrumented runs only: how many shadow rays carry a non-zero BSDF
+        BSDFEval probe = material_eval(mat, wo_l, world_to_local(it.geom.onb, ls.wi));
+        V3 a = beta * probe.bsdf, b = ls.eval.L * (1.f / (probe.pdf + ls.eval.pdf));
+        // fma(0, finite, L) == L: such a connection cannot change the image
+        bool null_contrib = a.x == 0.f && a.y == 0.f && a.z == 0.f && std::isfinite(b.x) && std::isfinite(b.y) && std::isfinite(b.z);
+        if (!null_contrib) ps.shadow_nonnull++;
+      }
+      if (!scene_any<COUNT>(s, shadow, dist - 1e-3f, cs)) {
+        BSDFEval fe = material_eval(mat, wo_l, world_to_local(it.geom.onb, ls.wi));  // EvalBSDF, Primitive.fs:83-84
+        L = vfma(beta * fe.bsdf, ls.eval.L * (1.f / (fe.pdf + ls.eval.pdf)), L);
+      }
+    }
+    float ulobe = sampler.next1d();
+    V2 ub = sampler.next2d();
+    BSDFSample bs = material_sample(mat, wo_l, ulobe, ub);  // :61 (Interaction.SampleBSDF, Primitive.fs:86-89)
+    bs.wi = local_to_world(it.geom.onb, bs.wi);
+    prev_bsdf_pdf = bs.eval.pdf;
+    if (bs.eval.pdf == 0.f) { depth = max_depth; continue; }  // :63-64
+    ray = {it.geom.p, bs.wi};
+    beta = beta * bs.eval.bsdf * (1.f / bs.eval.pdf);
+    if (depth >= rr_depth) {  // :69-75
+      float q = net_min(1.f, net_max(beta.x, net_max(beta.y, beta.z)));
+      if (sampler.next1d() < q) beta = beta * (1.f / q);
+      else depth = max_depth;
+    }
+    depth++;
+  }
+  return L;
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI of the oracle (loaded with ctypes by tests/ and bench.py only)
+// =============================================================================
+struct BoScene { Scene s; };
+
+extern "C" {
+
+#define BO_API __attribute__((visibility("default")))
+
+BO_API void bo_set_portable_math(int on) { g_portable_math = on ? 1 : 0; }
+BO_API int bo_get_portable_math(void) { return g_portable_math; }
+
+BO_API uint32_t bo_xxhash32_two(uint32_t x, uint32_t y) { return xxhash32_two(x, y); }
+BO_API uint32_t bo_xxhash32_three(uint32_t x, uint32_t y, uint32_t z) { return xxhash32_three(x, y, z); }
+BO_API float bo_lcg(uint32_t* state) { return lcg(*state); }
+
+BO_API void bo_sincos(float x, float* s, float* c) { o_sincos(x, *s, *c); }
+BO_API float bo_atan(float x) { return o_atan(x); }
+
+BO_API int bo_scene_create(const BnSceneDesc* d, BoScene** out) {
+  if (!d || !out) return -1;
+  auto* b = new BoScene();
+  Scene& s = b->s;
+  s.tlas.assign(d->tlas_nodes, d->tlas_nodes + d->tlas_node_count);
+  s.blas.assign(d->blas_nodes, d->blas_nodes + d->blas_node_count);
+  s.inst.assign(d->instances, d->instances + d->instance_count);
+  s.light_inst.assign(d->light_instances, d->light_instances + d->light_instance_count);
+  s.meshes.assign(d->meshes, d->meshes + d->mesh_count);
+  s.verts.assign(d->vertices, d->vertices + (size_t)d->vertex_count * 3);
+  s.tris.assign(d->triangles, d->triangles + (size_t)d->triangle_count * 3);
+  s.alias.assign(d->alias, d->alias + d->alias_count);
+  s.radii.assign(d->sphere_radii, d->sphere_radii + d->sphere_count);
+  s.mats.assign(d->materials, d->materials + d->material_count);
+  s.lights.assign(d->lights, d->lights + d->light_count);
+  s.cam = d->camera;
+  *out = b;
+  return 0;
+}
+BO_API void bo_scene_destroy(BoScene* s) { delete s; }
+
+// counters: [tlas_nodes, blas_nodes, tris_fetched, tris_box_pass, inst_visited, inst_box_pass, inst_committed, rays]
+static void export_counters(const Counters& c, uint64_t* out) {
+  out[0] = c.tlas_nodes; out[1] = c.blas_nodes; out[2] = c.tris_fetched; out[3] = c.tris_box_pass;
+  out[4] = c.inst_visited; out[5] = c.inst_box_pass; out[6] = c.inst_committed; out[7] = c.rays;
+}
+
+// PrimitiveAggregate.Intersect on a fixed batch.  counters (8 x u64) may be NULL.
+BO_API int bo_trace(const BoScene* sc, const BnRay* rays, uint64_t n, int any_hit, BnHit* hits, uint64_t* counters, int threads) {
+  if (!sc || !rays || !hits) return -1;
+  const Scene& s = sc->s;
+  Counters total;
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+  {
+    Counters c;
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+      Ray ray{load3(rays[i].origin), load3(rays[i].direction)};
+      BnHit h{};
+      if (any_hit) {
+        bool hit = counters ? scene_any<true>(s, ray, rays[i].tmax, &c) : scene_any<false>(s, ray, rays[i].tmax, &c);
+        h.t = 0.f; h.u = 0.f; h.v = 0.f; h.instance = hit ? 1 : 0; h.primitive = 0;
+      } else {
+        Interaction it{};
+        float t = rays[i].tmax;
+        bool hit = counters ? scene_closest<true>(s, ray, it, t, &c) : scene_closest<false>(s, ray, it, t, &c);
+        h.t = t;
+        if (hit) { h.u = it.geom.uv.x; h.v = it.geom.uv.y; h.instance = it.inst; h.primitive = it.geom.prim; }
+        else { h.u = 0.f; h.v = 0.f; h.instance = -1; h.primitive = -1; }
+      }
+      hits[i] = h;
+    }
+#pragma omp critical
+    total.add(c);
+  }
+  if (counters) export_counters(total, counters);
+  return 0;
+}
+
+// World-space interaction of a closest hit (for shading parity / debugging):
+// out = p[3], n[3], t[3], b[3]
+BO_API int bo_closest_geom(const BoScene* sc, const BnRay* ray, float* out) {
+  Interaction it{};
+  float t = ray->tmax;
+  Counters c;
+  Ray r{load3(ray->origin), load3(ray->direction)};
+  if (!scene_closest<false>(sc->s, r, it, t, &c)) return 0;
+  const Geom& g = it.geom;
+  float v[12] = {g.p.x, g.p.y, g.p.z, g.onb.n.x, g.onb.n.y, g.onb.n.z, g.onb.t.x, g.onb.t.y, g.onb.t.z, g.onb.b.x, g.onb.b.y, g.onb.b.z};
+  std::memcpy(out, v, sizeof v);
+  return 1;
+}
+
+// Primary rays of (x, y, sampleId) — Integrator.fs:34-39
+BO_API int bo_primary_rays(const BoScene* sc, const BnRenderParams* p, BnRay* out) {
+  const Scene& s = sc->s;
+  size_t k = 0;
+  for (int sm = p->sample_begin; sm < p->sample_end; ++sm)
+    for (int y = p->y0; y < p->y1; ++y)
+      for (int x = p->x0; x < p->x1; ++x) {
+        Sampler sp{xxhash32_three((uint32_t)x, (uint32_t)y, (uint32_t)(p->frame_id * p->spp + sm))};
+        V2 up = sp.next2d();
+        V2 ul = sp.next2d();
+        Ray r = primary_ray(s.cam, p->width, p->height, x, y, up, ul);
+        BnRay o{{r.o.x, r.o.y, r.o.z}, {r.d.x, r.d.y, r.d.z}, kInf};
+        out[k++] = o;
+      }
+  return 0;
+}
+
+// Per-path radiance, layout [sample - sample_begin][(y - y0)*(x1-x0) + (x - x0)][3]
+BO_API int bo_render_radiance(const BoScene* sc, const BnRenderParams* p, float* radiance, int threads) {
+  const Scene& s = sc->s;
+  if (s.light_inst.empty()) return BN_ERR_NO_LIGHT;
+  if (threads <= 0) threads = omp_get_max_threads();
+  const int rw = p->x1 - p->x0, rh = p->y1 - p->y0;
+  const int64_t npix = (int64_t)rw * rh;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+  for (int64_t i = 0; i < npix; ++i) {
+    int x = p->x0 + (int)(i % rw), y = p->y0 + (int)(i / rw);
+    for (int sm = p->sample_begin; sm < p->sample_end; ++sm) {
+      Sampler sp{xxhash32_three((uint32_t)x, (uint32_t)y, (uint32_t)(p->frame_id * p->spp + sm))};
+      V2 up = sp.next2d();
+      V2 ul = sp.next2d();
+      Ray ray = primary_ray(s.cam, p->width, p->height, x, y, up, ul);
+      PathStats ps;
+      V3 L = path_li<false>(s, ray, sp, p->max_depth, p->rr_depth, ps, nullptr, nullptr) * (1.f / 1.f);
+      float* o = radiance + ((int64_t)(sm - p->sample_begin) * npix + i) * 3;
+      o[0] = L.x; o[1] = L.y; o[2] = L.z;
+    }
+  }
+  return 0;
+}
+
+// ProgressiveIntegrator.Render — Integrator.fs:22-55: 16x16 tiles, dynamic
+// scheduling over the host threads (Parallel.ForEach -> OpenMP schedule(dynamic)),
+// per pixel accum = fma(1/spp, radiance, accum), Film.SetPixel (Y flip, Film.fs:41-46).
+// stats (may be NULL): [paths, extend_rays, shadow_rays, shadow_rays_nonnull, seconds*1e6]
+// counters_extend / counters_shadow (8 x u64 each, may be NULL) switch on the
+// instrumented traversal (slower; never used for timing).
+BO_API int bo_render(const BoScene* sc, const BnRenderParams* p, float* film, uint64_t* stats,
+                     uint64_t* counters_extend, uint64_t* counters_shadow, int threads) {
+  if (!sc || !p || !film) return -1;
+  const Scene& s = sc->s;
+  if (s.light_inst.empty()) return BN_ERR_NO_LIGHT;
+  if (threads <= 0) threads = omp_get_max_threads();
+  const int W = p->width, H = p->height, tile = 16;
+  std::memset(film, 0, sizeof(float) * 3 * (size_t)W * H);
+  const int txc = (W + tile - 1) / tile, tyc = (H + tile - 1) / tile;
+  const float inv_spp = 1.f / (float)p->spp;
+  const bool instrument = counters_extend || counters_shadow;
+  PathStats total;
+  Counters tce, tcs;
+  auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel num_threads(threads)
+  {
+    PathStats ps;
+    Counters ce, cs;
+#pragma omp for schedule(dynamic, 1)
+    for (int tid = 0; tid < txc * tyc; ++tid) {
+      int tx = tid % txc, ty = tid / txc;
+      int xf = std::max(tx * tile, p->x0), yf = std::max(ty * tile, p->y0);
+      int xl = std::min(std::min((tx + 1) * tile, W), p->x1), yl = std::min(std::min((ty + 1) * tile, H), p->y1);
+      for (int y = yf; y < yl; ++y)
+        for (int x = xf; x < xl; ++x) {
+          V3 accum{0, 0, 0};
+          for (int sm = p->sample_begin; sm < p->sample_end; ++sm) {
+            Sampler sp{xxhash32_three((uint32_t)x, (uint32_t)y, (uint32_t)(p->frame_id * p->spp + sm))};
+            V2 up = sp.next2d();
+            V2 ul = sp.next2d();
+            Ray ray = primary_ray(s.cam, W, H, x, y, up, ul);
+            V3 li = instrument ? path_li<true>(s, ray, sp, p->max_depth, p->rr_depth, ps, &ce, &cs)
+                               : path_li<false>(s, ray, sp, p->max_depth, p->rr_depth, ps, &ce, &cs);
+            V3 radiance = li * (1.f / 1.f);  // camera pdf is 1 (Pinhole.fs:27)
+            accum = vfma(splat(inv_spp), radiance, accum);
+          }
+          float* px = film + ((size_t)(H - y - 1) * W + x) * 3;
+          px[0] = accum.x; px[1] = accum.y; px[2] = accum.z;
+        }
+    }
+#pragma omp critical
+    {
+      total.extend += ps.extend; total.shadow += ps.shadow; total.shadow_nonnull += ps.shadow_nonnull;
+      tce.add(ce); tcs.add(cs);
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  if (stats) {
+    int rw = std::max(0, std::min(p->x1, W) - std::max(p->x0, 0)), rh = std::max(0, std::min(p->y1, H) - std::max(p->y0, 0));
+    stats[0] = (uint64_t)rw * rh * (uint64_t)std::max(0, p->sample_end - p->sample_begin);
+    stats[1] = total.extend; stats[2] = total.shadow; stats[3] = total.shadow_nonnull;
+    stats[4] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+  }
+  if (counters_extend) export_counters(tce, counters_extend);
+  if (counters_shadow) export_counters(tcs, counters_shadow);
+  return 0;
+}
+
+BO_API int bo_num_threads(void) { return omp_get_max_threads(); }
+
+}  // extern "C"

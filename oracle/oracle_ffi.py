@@ -1,0 +1,128 @@
+"""ctypes loader for the ORACLE (oracle/libbarnacle_oracle.so).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package never
+imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbarnacle_oracle.so")
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("tmax", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("instance", "<i4"), ("primitive", "<i4")])
+COUNTER_NAMES = ["tlas_nodes", "blas_nodes", "tris_fetched", "tris_box_pass", "inst_visited", "inst_box_pass", "inst_committed", "rays"]
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "barnacle_oracle.cpp")
+    deps = [src, os.path.join(_HERE, "..", "include", "barnacle_b200.h"), os.path.join(_HERE, "..", "include", "bn_portable_math.h")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        lib = C.CDLL(LIB_PATH)
+        lib.bo_xxhash32_two.restype = C.c_uint32
+        lib.bo_xxhash32_two.argtypes = [C.c_uint32, C.c_uint32]
+        lib.bo_xxhash32_three.restype = C.c_uint32
+        lib.bo_xxhash32_three.argtypes = [C.c_uint32] * 3
+        lib.bo_lcg.restype = C.c_float
+        lib.bo_lcg.argtypes = [C.POINTER(C.c_uint32)]
+        lib.bo_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        lib.bo_atan.restype = C.c_float
+        lib.bo_atan.argtypes = [C.c_float]
+        lib.bo_scene_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.bo_scene_destroy.argtypes = [C.c_void_p]
+        lib.bo_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        lib.bo_closest_geom.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.bo_primary_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.bo_render_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.bo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.bo_set_portable_math.argtypes = [C.c_int]
+        _lib = lib
+    return _lib
+
+
+class OracleScene:
+    """CPU restatement of BVHAggregate + UniformLightSampler + PathTracingIntegrator
+    over a BnSceneDesc (any object exposing `.desc`, a ctypes pointer to it)."""
+
+    def __init__(self, desc_ptr):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.bo_scene_create(C.cast(desc_ptr, C.c_void_p), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("bo_scene_create failed")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bo_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def trace(self, rays: np.ndarray, any_hit: bool = False, counters: bool = False, threads: int = 0):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        cnt = np.zeros(8, dtype=np.uint64) if counters else None
+        rc = self._lib.bo_trace(self._h, rays.ctypes.data, rays.shape[0], 1 if any_hit else 0, hits.ctypes.data,
+                                cnt.ctypes.data if counters else None, threads)
+        assert rc == 0
+        return (hits, dict(zip(COUNTER_NAMES, (int(x) for x in cnt)))) if counters else hits
+
+    def closest_geom(self, ray: np.ndarray):
+        ray = np.ascontiguousarray(ray, dtype=RAY_DTYPE)
+        out = np.zeros(12, dtype=np.float32)
+        hit = self._lib.bo_closest_geom(self._h, ray.ctypes.data, out.ctypes.data)
+        return bool(hit), out.reshape(4, 3)
+
+    def primary_rays(self, params) -> np.ndarray:
+        n = (params.sample_end - params.sample_begin) * (params.y1 - params.y0) * (params.x1 - params.x0)
+        out = np.empty(n, dtype=RAY_DTYPE)
+        self._lib.bo_primary_rays(self._h, C.byref(params), out.ctypes.data)
+        return out
+
+    def render_radiance(self, params, threads: int = 0) -> np.ndarray:
+        ns = params.sample_end - params.sample_begin
+        out = np.empty((ns, params.y1 - params.y0, params.x1 - params.x0, 3), dtype=np.float32)
+        rc = self._lib.bo_render_radiance(self._h, C.byref(params), out.ctypes.data, threads)
+        assert rc == 0, rc
+        return out
+
+    def render(self, params, threads: int = 0, counters: bool = False):
+        """Returns (film [H*W,3], stats dict)."""
+        film = np.empty((params.height * params.width, 3), dtype=np.float32)
+        st = np.zeros(5, dtype=np.uint64)
+        ce = np.zeros(8, dtype=np.uint64) if counters else None
+        cs = np.zeros(8, dtype=np.uint64) if counters else None
+        rc = self._lib.bo_render(self._h, C.byref(params), film.ctypes.data, st.ctypes.data,
+                                 ce.ctypes.data if counters else None, cs.ctypes.data if counters else None, threads)
+        assert rc == 0, rc
+        stats = {"paths": int(st[0]), "extend_rays": int(st[1]), "shadow_rays": int(st[2]), "shadow_rays_nonnull": int(st[3]),
+                 "seconds": int(st[4]) * 1e-6}
+        if counters:
+            stats["extend_counters"] = dict(zip(COUNTER_NAMES, (int(x) for x in ce)))
+            stats["shadow_counters"] = dict(zip(COUNTER_NAMES, (int(x) for x in cs)))
+        return film, stats
+
+
+def set_portable_math(on: bool) -> None:
+    load().bo_set_portable_math(1 if on else 0)
+
+
+def num_threads() -> int:
+    return load().bo_num_threads()
