@@ -18,6 +18,7 @@ BN_PRIM_MESH, BN_PRIM_SPHERE = 0, 1
 BN_MAT_LAMBERTIAN, BN_MAT_MIRROR, BN_MAT_DIELECTRIC, BN_MAT_PBR = 0, 1, 2, 3
 BN_CAM_PINHOLE, BN_CAM_THIN_LENS = 0, 1
 BN_RENDER_TRACE_NULL_SHADOW = 1
+BN_RENDER_PROFILE = 2
 
 
 class BnBVHNode(C.Structure):
@@ -72,7 +73,8 @@ class BnSceneDesc(C.Structure):
 class BnRenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
                 ("rr_depth", C.c_int32), ("frame_id", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32),
-                ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32), ("flags", C.c_uint32)]
+                ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32), ("flags", C.c_uint32),
+                ("interleave_count", C.c_int32), ("interleave_index", C.c_int32)]
 
 
 class BnStats(C.Structure):

@@ -49,6 +49,7 @@ struct WaveParams {
   int n_samples;      // samples per pixel in this wave
   uint32_t flags;
   float inv_spp;
+  int il_count, il_index;  // tile-row interleave (BnRenderParams.interleave_*)
 };
 
 // ---- warp helpers --------------------------------------------------------------
@@ -73,7 +74,9 @@ BN_DEV void wave_pixel(const WaveParams& wp, int pl, int& x, int& y) {
   const int block = wp.block_begin + (pl >> 5);
   const int lane = pl & 31;
   x = wp.x0 + (block % wp.nbx) * 8 + (lane & 7);
-  y = wp.y0 + (block / wp.nbx) * 4 + (lane >> 3);
+  const int brow = block / wp.nbx;  // 4-pixel block row among the rows this call owns
+  const int tile_row = (brow >> 2) * wp.il_count + wp.il_index;
+  y = wp.y0 + tile_row * 16 + (brow & 3) * 4 + (lane >> 3);
 }
 
 // ---- raygen: RenderTile's sample loop head (Integrator.fs:34-39) ------------------
@@ -374,6 +377,7 @@ struct BnScene {
   float* film = nullptr;
   size_t film_len = 0;
   bool poisoned = false;
+  std::vector<cudaEvent_t> events;  // BN_RENDER_PROFILE: start/stop pairs, one per kernel launch
 };
 
 namespace {
@@ -422,7 +426,8 @@ int ensure_wave_buffers(BnScene* s, size_t cap) {
 
 int validate_params(const BnRenderParams* p) {
   if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth < 0 || p->sample_begin < 0 || p->sample_end > p->spp ||
-      p->sample_begin > p->sample_end || p->x0 < 0 || p->y0 < 0 || p->x1 > p->width || p->y1 > p->height || p->x0 > p->x1 || p->y0 > p->y1) {
+      p->sample_begin > p->sample_end || p->x0 < 0 || p->y0 < 0 || p->x1 > p->width || p->y1 > p->height || p->x0 > p->x1 || p->y0 > p->y1 ||
+      (p->interleave_count > 1 && (p->interleave_index < 0 || p->interleave_index >= p->interleave_count))) {
     bnhost::set_error("bn_render: invalid BnRenderParams");
     return BN_ERR_INVALID;
   }
@@ -436,7 +441,10 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
   if (s->d.n_light_inst == 0) { bnhost::set_error("LightSamplerBase: No light primitives found."); return BN_ERR_NO_LIGHT; }
   BN_CUDA(cudaSetDevice(s->device));
   const int rw = p->x1 - p->x0, rh = p->y1 - p->y0, ns = p->sample_end - p->sample_begin;
-  const int nbx = (rw + 7) / 8, nby = (rh + 3) / 4;
+  const int il_count = p->interleave_count > 1 ? p->interleave_count : 1, il_index = il_count > 1 ? p->interleave_index : 0;
+  const int tile_rows = (rh + 15) / 16;
+  const int owned_rows = tile_rows > il_index ? (tile_rows - il_index + il_count - 1) / il_count : 0;
+  const int nbx = (rw + 7) / 8, nby = il_count > 1 ? owned_rows * 4 : (rh + 3) / 4;
   const long long total_blocks = (long long)nbx * nby;
   uint64_t launches = 0;
   cudaEvent_t ev0, ev1;
@@ -469,6 +477,27 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     BN_CUDA(cudaMemsetAsync(s->counters, 0, need * sizeof(int), stream));
     BN_CUDA(cudaMemsetAsync(s->shadow_ref, 0, sizeof(unsigned long long), stream));
     const int grid = s->num_sms * 8;
+    // BN_RENDER_PROFILE: bracket every launch with events on the launching stream
+    const bool profile = (p->flags & BN_RENDER_PROFILE) != 0 && stats != nullptr;
+    std::vector<int> ev_class;  // 0 extend, 1 shade, 2 shadow, 3 other
+    size_t ev_used = 0;
+    auto prof_begin = [&](int cls) {
+      if (!profile) return;
+      if (s->events.size() < ev_used + 2) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        s->events.push_back(a);
+        s->events.push_back(b);
+      }
+      ev_class.push_back(cls);
+      cudaEventRecord(s->events[ev_used], stream);
+    };
+    auto prof_end = [&]() {
+      if (!profile) return;
+      cudaEventRecord(s->events[ev_used + 1], stream);
+      ev_used += 2;
+    };
     long long wave = 0;
     for (long long bc = 0; bc < n_block_chunks; ++bc) {
       for (long long scn = 0; scn < n_sample_chunks; ++scn, ++wave) {
@@ -481,6 +510,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         wp.n_samples = std::min(samples_per_wave, p->sample_end - wp.sample_begin);
         wp.flags = p->flags;
         wp.inv_spp = 1.0f / (float)p->spp;  // MathF.ReciprocalEstimate restated as IEEE 1/x
+        wp.il_count = il_count; wp.il_index = il_index;
         int* base = s->counters + per_wave * (size_t)wave;
         int* n_active = base;
         int* n_shadow = base + (D + 1);
@@ -488,19 +518,29 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         const size_t cp = s->cap;
         float4* A = s->state[0];
         float4* B = s->state[1];
+        prof_begin(3);
         k_raygen<<<grid, kBlock, 0, stream>>>(s->d, wp, A, A + cp, A + 2 * cp, s->rad, n_active);
+        prof_end();
         ++launches;
         for (int b = 0; b < D; ++b) {
+          prof_begin(0);
           k_extend<<<grid, kBlock, 0, stream>>>(s->d, A, A + cp, s->hits, n_active + b, cursors + 3 * b);
+          prof_end();
+          prof_begin(1);
           k_shade<<<grid, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
                                                s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b, n_active + b + 1, n_shadow + b,
                                                cursors + 3 * b + 1, s->shadow_ref);
+          prof_end();
+          prof_begin(2);
           k_shadow<<<grid, kBlock, 0, stream>>>(s->d, s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b, cursors + 3 * b + 2);
+          prof_end();
           launches += 3;
           std::swap(A, B);
         }
+        prof_begin(3);
         if (d_radiance) k_export_radiance<<<grid, kBlock, 0, stream>>>(wp, s->rad, d_radiance, p->sample_begin);
         else k_accumulate<<<grid, kBlock, 0, stream>>>(wp, s->rad, d_film);
+        prof_end();
         ++launches;
       }
     }
@@ -520,18 +560,24 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
       unsigned long long ref = 0;
       BN_CUDA(cudaMemcpy(&ref, s->shadow_ref, sizeof ref, cudaMemcpyDeviceToHost));
       stats->paths = n_paths; stats->extend_rays = ext; stats->shadow_rays = sh; stats->shadow_rays_ref = ref;
+      stats->extend_ms = stats->shade_ms = stats->shadow_ms = stats->other_ms = 0.0;
+      for (size_t k = 0; k < ev_class.size(); ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->events[2 * k], s->events[2 * k + 1]);
+        double* dst = ev_class[k] == 0 ? &stats->extend_ms : (ev_class[k] == 1 ? &stats->shade_ms : (ev_class[k] == 2 ? &stats->shadow_ms : &stats->other_ms));
+        *dst += ms;
+      }
     }
   } else {
     BN_CUDA(cudaEventRecord(ev1, stream));
     BN_CUDA(cudaStreamSynchronize(stream));
-    if (stats) { stats->paths = 0; stats->extend_rays = 0; stats->shadow_rays = 0; stats->shadow_rays_ref = 0; }
+    if (stats) { stats->paths = 0; stats->extend_rays = 0; stats->shadow_rays = 0; stats->shadow_rays_ref = 0; stats->extend_ms = stats->shade_ms = stats->shadow_ms = stats->other_ms = 0.0; }
   }
   if (stats) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     stats->gpu_ms = ms;
     stats->kernel_launches = launches;
-    stats->extend_ms = stats->shade_ms = stats->shadow_ms = stats->other_ms = 0.0;
   }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
@@ -586,6 +632,7 @@ void bn_scene_destroy(BnScene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
+  for (cudaEvent_t e : s->events) cudaEventDestroy(e);
   for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->counters, (void*)s->shadow_ref, (void*)s->film})
     if (p) cudaFree(p);
   delete s;
@@ -625,6 +672,7 @@ int bn_render_radiance(BnScene* s, const BnRenderParams* p, float* radiance) {
   if (len == 0) return BN_OK;
   float* d = nullptr;
   BN_CUDA(cudaMalloc((void**)&d, len * sizeof(float)));
+  BN_CUDA(cudaMemset(d, 0, len * sizeof(float)));
   rc = render_waves(s, p, nullptr, d, nullptr, nullptr);
   if (rc == BN_OK && !cuda_ok(cudaMemcpy(radiance, d, len * sizeof(float), cudaMemcpyDeviceToHost), "copy radiance")) rc = BN_ERR_CUDA;
   cudaFree(d);

@@ -39,6 +39,10 @@ class RenderStats:
     shadow_rays_ref: int
     kernel_launches: int
     gpu_ms: float
+    extend_ms: float = 0.0
+    shade_ms: float = 0.0
+    shadow_ms: float = 0.0
+    other_ms: float = 0.0
 
     @property
     def rays(self) -> int:
@@ -46,10 +50,10 @@ class RenderStats:
 
 
 def make_params(width, height, spp, max_depth=8, rr_depth=5, frame_id=0, sample_begin=0, sample_end=None,
-                rect=None, flags=0) -> BnRenderParams:
+                rect=None, flags=0, interleave=(1, 0)) -> BnRenderParams:
     x0, y0, x1, y1 = rect if rect is not None else (0, 0, width, height)
     return BnRenderParams(width, height, spp, max_depth, rr_depth, frame_id, sample_begin,
-                          spp if sample_end is None else sample_end, x0, y0, x1, y1, flags)
+                          spp if sample_end is None else sample_end, x0, y0, x1, y1, flags, interleave[0], interleave[1])
 
 
 class Film:
@@ -105,7 +109,8 @@ class GpuScene:
 
     @staticmethod
     def _stats(st: BnStats) -> RenderStats:
-        return RenderStats(st.paths, st.extend_rays, st.shadow_rays, st.shadow_rays_ref, st.kernel_launches, st.gpu_ms)
+        return RenderStats(st.paths, st.extend_rays, st.shadow_rays, st.shadow_rays_ref, st.kernel_launches, st.gpu_ms,
+                           st.extend_ms, st.shade_ms, st.shadow_ms, st.other_ms)
 
     def render(self, params: BnRenderParams, film: np.ndarray | None = None):
         """bn_render: host film (W*H*3 fp32, Film.Pixels layout); returns (film, stats)."""

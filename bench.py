@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""bench.py — the hot path's headline measurement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch: one full frame of the named
+workload (default C2 = BASELINE.json configs[1]: Cornell box + Stanford bunny,
+1024x1024, 256 spp) — raygen -> extend -> shade -> shadow -> accumulate for every
+(pixel, sampleId).  The scene is synthetic in the sense of the contract: authored
+in the reference's schema by scenes/make_scenes.py, seeds fully determined by
+(x, y, sampleId).
+
+metric  Mrays/s = (closest-hit + any-hit rays actually traced) / device time.
+value   whole-job rate with the scene already resident in HBM and the film left in
+        HBM (bn_render_device), CUDA events, max over ranks.
+e2e     the same metric through the reference-facing C-ABI with HOST buffers
+        (bn_scene_create from host arrays + bn_render into a host film): host->device
+        copy of the flattened scene and device->host read of the film inside the
+        timed region.
+N > 1   launched by torchrun, one rank per GPU; the fixed frame is split by sample
+        index (strong scaling), one NCCL sum-reduce of the fp32 film to rank 0.
+--impl reference   the reference's CPU path (the C++ restatement in oracle/; the .NET
+        binary cannot run in this image) on all host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene file, width, height, spp, label)
+    "C1": ("cbox_pt.json", 512, 512, 64, "C1 cbox path-tracing 512x512x64spp"),
+    "C2": ("cbox_bunny.json", 1024, 1024, 256, "C2 cbox+stanford-bunny 1024x1024x256spp"),
+    "C3": ("material_sweep.json", 1920, 1080, 1024, "C3 GGX+dielectric sweep 1920x1080x1024spp"),
+    "C4": ("bunny_instanced.json", 3840, 2160, 512, "C4 4096 bunny instances 3840x2160x512spp"),
+}
+MAX_DEPTH, RR_DEPTH = 8, 5
+# algorithmic bytes per traced ray in the REFERENCE layout
+B_NODE, B_TRI, B_INST, B_IO_EXTEND, B_IO_SHADOW = 32, 48, 152, 48, 32
+
+
+def algorithmic_bytes_per_ray(c: dict, io: int) -> float:
+    rays = max(c["rays"], 1)
+    return (B_NODE * (c["tlas_nodes"] + c["blas_nodes"]) + B_TRI * c["tris_fetched"] + B_INST * c["inst_visited"]) / rays + io
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 8] or [r for (_, r) in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[4 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def oracle_sample(scene, w, h, spp_sample, counters: bool, libm: bool = True):
+    """The CPU restatement on a bounded sample of the workload (all host threads)."""
+    from barnacle_b200.scene import make_params
+    from oracle.oracle_ffi import OracleScene, num_threads, set_portable_math
+    set_portable_math(not libm)
+    try:
+        o = OracleScene(scene.desc)
+        p = make_params(w, h, spp_sample, MAX_DEPTH, RR_DEPTH)
+        _, st = o.render(p, counters=counters)
+    finally:
+        set_portable_math(True)
+    st["threads"] = num_threads()
+    return st
+
+
+def run_reference(args, scene_file, W, H, SPP, label):
+    """--impl reference: the reference's CPU renderer (C++ restatement, libm math, 16x16
+    tiles scheduled dynamically over all host threads), each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from barnacle_b200.scene import Scene
+    scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
+    spp_s = max(1, args.ref_spp)
+    for _ in range(args.warmup):
+        oracle_sample(scene, W, H, 1, False)
+    rays = secs = paths = 0
+    threads = 0
+    for _ in range(args.steps):
+        st = oracle_sample(scene, W, H, spp_s, False)
+        rays += st["extend_rays"] + st["shadow_rays"]
+        paths += st["paths"]
+        secs += st["seconds"]
+        threads = st["threads"]
+    val = rays / secs / 1e6
+    sample = f"{W}x{H} at {spp_s} of {SPP} spp per step (rates are spp-independent); rays = extend + shadow rays the reference traces"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": label, "max_depth": MAX_DEPTH, "rr_depth": RR_DEPTH},
+        "samples_per_s": paths / secs,
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of Barnacle's CPU path (the .NET binary is not runnable in this image)"},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (the result is then NOT the named config)")
+    ap.add_argument("--ref-spp", type=int, default=4, help="--impl reference: spp of the bounded sample per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    scene_file, W, H, SPP, label = WORKLOADS[args.workload]
+    if args.spp:
+        SPP = args.spp
+        label += f" [spp overridden to {SPP}]"
+    if args.impl == "reference":
+        return run_reference(args, scene_file, W, H, SPP, label)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from barnacle_b200 import _ffi
+    from barnacle_b200.multi_gpu import partition, render_sharded
+    from barnacle_b200.scene import GpuScene, Scene, make_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
+    gpu = scene.gpu(local)
+    film = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    base = make_params(W, H, SPP, MAX_DEPTH, RR_DEPTH, flags=_ffi.BN_RENDER_PROFILE)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        flush.zero_()  # L2 flush between iterations
+        return render_sharded(gpu, base, film, dist if world > 1 else None, stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = {"extend": 0, "shadow": 0, "paths": 0, "launches": 0, "extend_ms": 0.0, "shade_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0}
+    step_ms = []
+    barrier()
+    for _ in range(args.steps):
+        ev0.record()
+        st = step()
+        ev1.record()
+        torch.cuda.synchronize()
+        step_ms.append(ev0.elapsed_time(ev1))
+        if st is not None:
+            tot["extend"] += st.extend_rays; tot["shadow"] += st.shadow_rays; tot["paths"] += st.paths; tot["launches"] += st.kernel_launches
+            tot["extend_ms"] += st.extend_ms; tot["shade_ms"] += st.shade_ms; tot["shadow_ms"] += st.shadow_ms; tot["other_ms"] += st.other_ms
+            tot["render_ms"] += st.gpu_ms
+    barrier()
+    t_wall1 = time.time()
+    # flush.zero_() is inside ev0..ev1; subtract nothing — it is ~0.1 ms of a multi-hundred-ms step and is reported in config
+    my_ms = float(sum(step_ms))
+    agg = torch.tensor([my_ms, tot["extend"], tot["shadow"], tot["paths"], tot["launches"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        total_ms = float(mx[0])
+    else:
+        total_ms = my_ms
+    rays_total = float(agg[1] + agg[2])
+    paths_total = float(agg[3])
+    launches_total = int(agg[4])
+    value = rays_total / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: through the C-ABI with host buffers (scene upload + film download per step)
+    host_film = torch.empty(W * H * 3, dtype=torch.float32).pin_memory()
+    host_film_np = host_film.numpy()
+    shard = partition(W, H, SPP, world, rank)
+    from barnacle_b200.multi_gpu import shard_params
+    sp = shard_params(make_params(W, H, SPP, MAX_DEPTH, RR_DEPTH), shard)
+    d = scene.desc.contents
+    h2d = (d.tlas_node_count + d.blas_node_count) * 32 + d.instance_count * 168 + d.vertex_count * 12 + d.triangle_count * 12 + d.alias_count * 12 + \
+        d.sphere_count * 4 + d.material_count * 24 + d.light_count * 16 + d.light_instance_count * 4 + ctypes.sizeof(_ffi.BnCamera)
+    d2h = W * H * 3 * 4
+
+    def e2e_step():
+        g2 = GpuScene(scene.desc, local)               # host arrays -> device (flatten + cudaMemcpy H2D)
+        try:
+            if world > 1:
+                st2 = g2.render_device(sp, film.data_ptr(), stream) if not shard.empty else None
+                if shard.empty:
+                    film.zero_()
+                dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    host_film.copy_(film, non_blocking=False)   # device -> pinned host
+            else:
+                _, st2 = g2.render(sp, host_film_np)            # bn_render: film lands in the host buffer
+        finally:
+            g2.close()
+        return st2
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_rays = 0
+    for _ in range(args.steps):
+        st2 = e2e_step()
+        if st2 is not None:
+            e2e_rays += st2.extend_rays + st2.shadow_rays
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = e2e_t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.SUM)
+        e2e_s = float(mx[0])
+    e2e_value = float(e2e_t[1]) / e2e_s / 1e6
+
+    if rank == 0:
+        clk = clocks.stop(t_wall0, t_wall1)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # algorithmic bytes per extend ray from the instrumented oracle on a bounded sample of this workload
+        cw, ch = max(64, W // 8), max(64, H // 8)
+        cst = oracle_sample(scene, cw, ch, 2, True, libm=False)
+        b_ext = algorithmic_bytes_per_ray(cst["extend_counters"], B_IO_EXTEND)
+        b_sh = algorithmic_bytes_per_ray(cst["shadow_counters"], B_IO_SHADOW)
+        ext_s = tot["extend_ms"] * 1e-3
+        achieved = tot["extend"] * b_ext / ext_s / 1e9 if ext_s > 0 else None
+        roofline = {"bound": "hbm", "kernel": "k_extend (closest-hit TLAS+BLAS traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_ray": b_ext, "rays_per_s": tot["extend"] / ext_s if ext_s > 0 else None,
+                    "kernel_share_of_step": tot["extend_ms"] / tot["render_ms"] if tot["render_ms"] else None,
+                    "shadow": {"algorithmic_bytes_per_ray": b_sh, "achieved": (tot["shadow"] * b_sh / (tot["shadow_ms"] * 1e-3) / 1e9) if tot["shadow_ms"] else None,
+                               "rays_per_s": tot["shadow"] / (tot["shadow_ms"] * 1e-3) if tot["shadow_ms"] else None},
+                    "rank0_class_ms_per_step": {k: tot[k + "_ms"] / args.steps for k in ("extend", "shade", "shadow", "other")},
+                    "note": "bytes/ray = 32*N_node + 48*N_tri + 152*N_inst + 48 I/O in the REFERENCE layout (SURVEY 8d), counted by the instrumented oracle "
+                            f"on {cw}x{ch}x2spp of this scene; scene data is L2-resident, so this is an algorithmic-traffic rate against the HBM copy peak"}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            # ~10-30 s of CPU work: 4 spp of the workload's film (libm math, as the reference)
+            cs = oracle_sample(scene, W, H, 4 if W * H <= (1 << 21) else 1, False)
+            cpu = {"value": (cs["extend_rays"] + cs["shadow_rays"]) / cs["seconds"] / 1e6, "unit": "Mrays/s", "cores": cs["threads"], "kind": "port",
+                   "samples_per_s": cs["paths"] / cs["seconds"],
+                   "sample": f"{W}x{H} at {4 if W * H <= (1 << 21) else 1} of {SPP} spp ({cs['seconds']:.1f} s); rays = extend + shadow rays the reference traces",
+                   "note": "C++ restatement of Barnacle's CPU path (the .NET binary is not runnable in this image)"}
+        out = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": label, "max_depth": MAX_DEPTH, "rr_depth": RR_DEPTH, "parallelism": f"sample-split x{world} + film reduce" if world > 1 else "single GPU",
+                       "l2_flush": "256 MiB memset between steps", "wave_paths": int(os.environ.get("BN_WAVE_PATHS", 4 << 20))},
+            "samples_per_s": paths_total / (total_ms * 1e-3),
+            "rays_per_step": rays_total / args.steps, "paths_per_step": paths_total / args.steps,
+            "gpu_launches": launches_total,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,13 +147,21 @@ typedef struct BnRenderParams {
   int32_t sample_begin, sample_end;
   int32_t x0, y0, x1, y1;
   uint32_t flags;             /* BN_RENDER_* */
+  /* tile-row interleave (multi-GPU tile split): of the 16-pixel tile rows of the
+   * window (the reference's tile size, Integrator.fs:16), counted from y0, only
+   * rows r with r % interleave_count == interleave_index are rendered.
+   * interleave_count <= 1 renders every row. */
+  int32_t interleave_count, interleave_index;
 } BnRenderParams;
 
 enum {
   BN_RENDER_DEFAULT = 0,
   /* trace NEE shadow rays even when the BSDF evaluates to exactly 0 (mirror /
    * dielectric): reference-equivalent ray counts, same image */
-  BN_RENDER_TRACE_NULL_SHADOW = 1u << 0
+  BN_RENDER_TRACE_NULL_SHADOW = 1u << 0,
+  /* bracket every kernel launch with CUDA events on the launching stream and
+   * report per-class device time in BnStats.{extend,shade,shadow,other}_ms */
+  BN_RENDER_PROFILE = 1u << 1
 };
 
 typedef struct BnStats {
