@@ -8,10 +8,14 @@
 namespace bn {
 
 // Child reference encoding (GNode.left/right, traversal stack entries)
-//   bit31 = 0 : interior node, bits 0..30 = GNode index within the current tree
-//   bit31 = 1 : leaf, bits 24..30 = item count (<=127), bits 0..23 = first item
-// TLAS-level stack entries additionally carry kTlasBit (bit 30 of the *entry*,
-// not of the node's child field) so a pop knows which space the ray is in.
+//   bit31 = 0 : interior node, bits 0..29 = GNode index within the current tree
+//   bit31 = 1 : leaf
+//        BLAS: bits 24..29 = triangle count (<= 63), bits 0..23 = first triangle
+//        TLAS: bits 0..29  = instance slot (every TLAS leaf is ONE instance, see
+//              scene_convert.cpp: a reference leaf of k instances becomes a chain
+//              of k-1 order-preserving pseudo nodes)
+// During traversal TLAS-level refs additionally carry kTlasBit (bit 30) so a pop
+// knows which space the ray is in.  GNode.axis == 3 means "always left first".
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kMaxLeafFirst = 1u << 24;
 
@@ -37,7 +41,7 @@ struct __align__(16) GTri {  // pre-gathered vertices of one BLAS-order triangle
 static_assert(sizeof(GTri) == 48, "GTri must be 48 B");
 
 struct __align__(16) GTree {  // root of a TLAS / BLAS
-  float bmin[3]; uint32_t root;       // root ref (leaf if the tree is a single leaf)
+  float bmin[3]; uint32_t root;       // root ref (a leaf ref if the tree is a single leaf / single instance)
   float bmax[3]; uint32_t node_base;  // first GNode of this tree in the shared node array
 };
 
@@ -49,7 +53,20 @@ struct __align__(16) GMesh {
   uint32_t pad;
 };
 
-struct __align__(16) GInstHead {  // fetched at every instance visit (48 B)
+// What "entering" an instance needs, in one 96-B record (no dependent
+// instance -> mesh fetch): WorldToObject, then the primitive's BLAS root.
+struct __align__(16) GInstTrav {
+  float w2o[12];                      // rows 1..4 x columns 1..3 of WorldToObject
+  float bmin[3]; uint32_t root;       // BLAS root bounds (MeshPrimitive.Bounds) + root ref | sphere: unused
+  float bmax[3]; uint32_t node_base;  // mesh's first GNode
+  uint32_t tri_base;                  // mesh's first GTri
+  uint32_t is_sphere;
+  float radius;
+  uint32_t pad;
+};
+static_assert(sizeof(GInstTrav) == 96, "GInstTrav must be 96 B");
+
+struct __align__(16) GInstHead {  // shading-side instance record (48 B)
   float bmin[3]; uint32_t kind_prim;  // bit31: sphere, low bits: mesh / sphere index
   float bmax[3]; int32_t material;    // -1 = none
   int32_t light;                      // -1 = none
@@ -74,6 +91,7 @@ struct GCamera {
 struct DScene {
   const GNode* nodes;        // TLAS nodes first, then every mesh's nodes
   GTree tlas;
+  const GInstTrav* inst_trav;
   const GInstHead* inst_head;
   const GMat43* inst_w2o;
   const GMat43* inst_o2w;
@@ -85,6 +103,7 @@ struct DScene {
   const GLight* lights;
   const uint32_t* light_inst;
   uint32_t n_inst, n_light_inst;
+  uint32_t all_finite;       // every box / vertex / matrix is finite: the fast slab path is exact (vecmath.cuh)
   GCamera cam;
 };
 

@@ -112,22 +112,27 @@ __global__ void __launch_bounds__(kBlock) k_raygen(DScene sc, WaveParams wp, flo
 }
 
 // ---- extend: closest hit for every live path ----------------------------------------
+struct ExtendIO {
+  const float4* __restrict__ s0;
+  const float4* __restrict__ s1;
+  float4* __restrict__ hits;
+  int n;
+  int* cur;
+  BN_DEV int count() const { return n; }
+  BN_DEV int* cursor() const { return cur; }
+  BN_DEV void load(int i, float3& o, float3& d, float& t) const {
+    const float4 a = s0[i], b = s1[i];
+    o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
+    t = CUDART_INF_F;  // PathTracing.fs:25
+  }
+  BN_DEV void store(int i, bool, float t, int inst, int prim, float, float) const {
+    hits[i] = make_float4(t, __int_as_float(inst), __int_as_float(prim), 0.f);
+  }
+};
 __global__ void __launch_bounds__(kBlock) k_extend(DScene sc, const float4* __restrict__ s0, const float4* __restrict__ s1,
                                                    float4* __restrict__ hits, const int* __restrict__ n_ptr, int* cursor) {
-  const int n = *n_ptr;
-  for (;;) {
-    const int base = warp_fetch(cursor);
-    if (base >= n) break;
-    const int i = base + lane_id();
-    if (i < n) {
-      const float4 a = s0[i], b = s1[i];
-      float t = CUDART_INF_F;  // PathTracing.fs:25
-      HitRec h;
-      trace<false>(sc, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), t, h);
-      hits[i] = make_float4(t, __int_as_float(h.inst), __int_as_float(h.prim), 0.f);
-    }
-    __syncwarp();
-  }
+  ExtendIO io{s0, s1, hits, *n_ptr, cursor};
+  traverse_persistent<false>(sc, io);
 }
 
 // ---- shade: one iteration of Li's loop body (PathTracing.fs:30-79) --------------------
@@ -257,27 +262,34 @@ __global__ void __launch_bounds__(kBlock) k_shade(DScene sc, WaveParams wp, int 
 }
 
 // ---- shadow: any hit + connect (PathTracing.fs:47-59) ----------------------------------
+struct ShadowIO {
+  const float4* __restrict__ q0;
+  const float4* __restrict__ q1;
+  const float4* __restrict__ q2;
+  const float4* __restrict__ q3;
+  float4* __restrict__ rad;
+  int n;
+  int* cur;
+  BN_DEV int count() const { return n; }
+  BN_DEV int* cursor() const { return cur; }
+  BN_DEV void load(int i, float3& o, float3& d, float& t) const {
+    const float4 a = q0[i], b = q1[i];
+    o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
+    t = b.z;
+  }
+  BN_DEV void store(int i, bool occluded, float, int, int, float, float) const {
+    if (occluded) return;
+    const float4 b = q1[i], c = q2[i], e = q3[i];
+    const int pid = __float_as_int(b.w);
+    const float4 L4 = rad[pid];
+    const float3 L = vfma(f3(c.x, c.y, c.z), f3(c.w, e.x, e.y), f3(L4.x, L4.y, L4.z));
+    rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
+  }
+};
 __global__ void __launch_bounds__(kBlock) k_shadow(DScene sc, const float4* __restrict__ q0, const float4* __restrict__ q1, const float4* __restrict__ q2,
                                                    const float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr, int* cursor) {
-  const int n = *n_ptr;
-  for (;;) {
-    const int base = warp_fetch(cursor);
-    if (base >= n) break;
-    const int i = base + lane_id();
-    if (i < n) {
-      const float4 a = q0[i], b = q1[i];
-      float t = b.z;
-      HitRec h;
-      if (!trace<true>(sc, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), t, h)) {
-        const float4 c = q2[i], e = q3[i];
-        const int pid = __float_as_int(b.w);
-        const float4 L4 = rad[pid];
-        const float3 L = vfma(f3(c.x, c.y, c.z), f3(c.w, e.x, e.y), f3(L4.x, L4.y, L4.z));
-        rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
-      }
-    }
-    __syncwarp();
-  }
+  ShadowIO io{q0, q1, q2, q3, rad, *n_ptr, cursor};
+  traverse_persistent<true>(sc, io);
 }
 
 // ---- accumulate: accum = fma(1/spp, radiance, accum); Film.SetPixel -------------------
@@ -318,39 +330,45 @@ __global__ void __launch_bounds__(kBlock) k_export_radiance(WaveParams wp, const
 
 // ---- fixed-batch traversal (bn_trace) -------------------------------------------------
 template <bool ANY>
-__global__ void __launch_bounds__(kBlock) k_trace(DScene sc, const BnRay* __restrict__ rays, unsigned long long n, BnHit* __restrict__ hits, unsigned long long* cursor) {
-  for (;;) {
-    unsigned long long base = 0;
-    if (lane_id() == 0) base = atomicAdd(cursor, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const unsigned long long i = base + lane_id();
-    if (i < n) {
-      const BnRay r = rays[i];
-      const float3 o = f3(r.origin[0], r.origin[1], r.origin[2]), d = f3(r.direction[0], r.direction[1], r.direction[2]);
-      float t = r.tmax;
-      HitRec h;
-      const bool hit = trace<ANY>(sc, o, d, t, h);
-      BnHit out;
-      if (ANY) {
-        out.t = 0.f; out.u = 0.f; out.v = 0.f; out.instance = hit ? 1 : 0; out.primitive = 0;
-      } else {
-        out.t = t; out.u = h.u; out.v = h.v; out.instance = h.inst; out.primitive = h.prim;
-        if (hit) {
-          const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.inst_head + h.inst));
-          if (__float_as_uint(h0.w) & 0x80000000u) {  // sphere uv (Sphere.fs:55-56), libdevice atan2/acos
-            const Mat43 M = load_mat43(reinterpret_cast<const float4*>(sc.inst_w2o + h.inst));
-            const float3 nn = normalize(point_at(transform_point(o, M), transform_dir(d, M), t));
-            out.u = atan2f(nn.z, nn.x) / (2.f * kPi) + 0.5f;
-            out.v = acosf(nn.y) / kPi;
-            out.primitive = 0;
-          }
+struct TraceIO {
+  DScene sc;
+  const BnRay* __restrict__ rays;
+  BnHit* __restrict__ hits;
+  int n;
+  int* cur;
+  BN_DEV int count() const { return n; }
+  BN_DEV int* cursor() const { return cur; }
+  BN_DEV void load(int i, float3& o, float3& d, float& t) const {
+    const BnRay r = rays[i];
+    o = f3(r.origin[0], r.origin[1], r.origin[2]); d = f3(r.direction[0], r.direction[1], r.direction[2]);
+    t = r.tmax;
+  }
+  BN_DEV void store(int i, bool hit, float t, int inst, int prim, float u, float v) const {
+    BnHit out;
+    if (ANY) {
+      out.t = 0.f; out.u = 0.f; out.v = 0.f; out.instance = hit ? 1 : 0; out.primitive = 0;
+    } else {
+      out.t = t; out.u = u; out.v = v; out.instance = inst; out.primitive = prim;
+      if (hit) {
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.inst_head + inst));
+        if (__float_as_uint(h0.w) & 0x80000000u) {  // sphere uv (Sphere.fs:55-56), libdevice atan2/acos
+          const BnRay r = rays[i];
+          const float3 o = f3(r.origin[0], r.origin[1], r.origin[2]), d = f3(r.direction[0], r.direction[1], r.direction[2]);
+          const Mat43 M = load_mat43(reinterpret_cast<const float4*>(sc.inst_w2o + inst));
+          const float3 nn = normalize(point_at(transform_point(o, M), transform_dir(d, M), t));
+          out.u = atan2f(nn.z, nn.x) / (2.f * kPi) + 0.5f;
+          out.v = acosf(nn.y) / kPi;
+          out.primitive = 0;
         }
       }
-      hits[i] = out;
     }
-    __syncwarp();
+    hits[i] = out;
   }
+};
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock) k_trace(DScene sc, const BnRay* __restrict__ rays, int n, BnHit* __restrict__ hits, int* cursor) {
+  TraceIO<ANY> io{sc, rays, hits, n, cursor};
+  traverse_persistent<ANY>(sc, io);
 }
 
 }  // namespace bn
@@ -612,7 +630,7 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   s->num_sms = prop.multiProcessorCount;
   int rc = BN_OK;
   DScene& d = s->d;
-  if ((rc = upload(s, cs.nodes, &d.nodes)) || (rc = upload(s, cs.inst_head, &d.inst_head)) || (rc = upload(s, cs.inst_w2o, &d.inst_w2o)) ||
+  if ((rc = upload(s, cs.nodes, &d.nodes)) || (rc = upload(s, cs.inst_trav, &d.inst_trav)) || (rc = upload(s, cs.inst_head, &d.inst_head)) || (rc = upload(s, cs.inst_w2o, &d.inst_w2o)) ||
       (rc = upload(s, cs.inst_o2w, &d.inst_o2w)) || (rc = upload(s, cs.meshes, &d.meshes)) || (rc = upload(s, cs.tris, &d.tris)) ||
       (rc = upload(s, cs.alias, &d.alias)) || (rc = upload(s, cs.sphere_radii, &d.sphere_radii)) || (rc = upload(s, cs.materials, &d.materials)) ||
       (rc = upload(s, cs.lights, &d.lights)) || (rc = upload(s, cs.light_inst, &d.light_inst))) {
@@ -622,6 +640,7 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   d.tlas = cs.tlas;
   d.n_inst = (uint32_t)cs.inst_head.size();
   d.n_light_inst = (uint32_t)cs.light_inst.size();
+  d.all_finite = cs.all_finite ? 1u : 0u;
   d.cam = cs.cam;
   if (cudaMalloc((void**)&s->shadow_ref, sizeof(unsigned long long)) != cudaSuccess) { bn_scene_destroy(s); bnhost::set_error("cudaMalloc failed"); return BN_ERR_CUDA; }
   *out = s;
@@ -684,17 +703,22 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
   if (s->poisoned) { bnhost::set_error("scene is unusable after an earlier CUDA error"); return BN_ERR_CUDA; }
   BN_CUDA(cudaSetDevice(s->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  unsigned long long* cursor = nullptr;
-  BN_CUDA(cudaMalloc((void**)&cursor, sizeof(unsigned long long)));
-  BN_CUDA(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
+  const uint64_t chunk = 1ull << 30;
+  const int n_chunks = (int)((n + chunk - 1) / chunk);
+  int* cursors = nullptr;
+  BN_CUDA(cudaMalloc((void**)&cursors, sizeof(int) * (size_t)std::max(n_chunks, 1)));
+  BN_CUDA(cudaMemsetAsync(cursors, 0, sizeof(int) * (size_t)std::max(n_chunks, 1), stream));
   cudaEvent_t e0, e1;
   BN_CUDA(cudaEventCreate(&e0));
   BN_CUDA(cudaEventCreate(&e1));
   BN_CUDA(cudaEventRecord(e0, stream));
   const int grid = s->num_sms * 8;
-  if (n) {
-    if (any_hit) k_trace<true><<<grid, kBlock, 0, stream>>>(s->d, static_cast<const BnRay*>(d_rays), n, static_cast<BnHit*>(d_hits), cursor);
-    else k_trace<false><<<grid, kBlock, 0, stream>>>(s->d, static_cast<const BnRay*>(d_rays), n, static_cast<BnHit*>(d_hits), cursor);
+  for (int c = 0; c < n_chunks; ++c) {
+    const BnRay* r = static_cast<const BnRay*>(d_rays) + (uint64_t)c * chunk;
+    BnHit* h = static_cast<BnHit*>(d_hits) + (uint64_t)c * chunk;
+    const int m = (int)std::min<uint64_t>(chunk, n - (uint64_t)c * chunk);
+    if (any_hit) k_trace<true><<<grid, kBlock, 0, stream>>>(s->d, r, m, h, cursors + c);
+    else k_trace<false><<<grid, kBlock, 0, stream>>>(s->d, r, m, h, cursors + c);
   }
   BN_CUDA(cudaEventRecord(e1, stream));
   cudaError_t e = cudaStreamSynchronize(stream);
@@ -703,7 +727,7 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
   if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  cudaFree(cursor);
+  cudaFree(cursors);
   if (e != cudaSuccess) { s->poisoned = true; cuda_ok(e, "bn_trace"); return BN_ERR_CUDA; }
   if (ms) *ms = t;
   return BN_OK;

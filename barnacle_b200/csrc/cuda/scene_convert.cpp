@@ -4,6 +4,7 @@
 // reference's op sequence gives.
 #include "scene_convert.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -17,32 +18,78 @@ using bnhost::V3;
 
 struct TreeOut {
   bn::GTree tree;
-  int depth = 0;
+  int depth = 0;     // GNode levels incl. the pseudo chains of TLAS leaves
   int max_leaf = 0;
+  bool finite = true;
 };
 
-bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_t node_base, std::vector<bn::GNode>& out, TreeOut& t, std::string& err,
-                const char* what) {
+bool finite3(const float* v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
+
+// Converts one reference BVH (preorder BnBVHNode array) into GNodes appended at
+// out[node_base...].  BLAS (instances == nullptr): a leaf becomes a leaf ref
+// (count, first triangle).  TLAS: every leaf ref is ONE instance whose world AABB
+// sits in its parent, so the traversal tests it like any child box; a reference
+// leaf holding k > 1 instances becomes a chain of k-1 pseudo nodes
+//     P1{ left = inst f, right = P2 } , P2{ left = inst f+1, right = ... }
+// with axis = 3 ("always left first") and +-FLT_MAX bounds for the chain links,
+// which visits the instances in slot order, each against the then-current t —
+// exactly the loop at Aggregate/BVH.fs:49-50 (a link fails only when t < 1e-3, and
+// then every instance test would fail too because tMin >= 1e-3).
+bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_t node_base, const BnInstance* instances,
+                std::vector<bn::GNode>& out, TreeOut& t, std::string& err, const char* what) {
   if (count == 0) { err = std::string(what) + ": empty BVH"; return false; }
   std::vector<int> gidx(count, -1);
   int next = 0;
-  for (uint32_t i = 0; i < count; ++i)
+  for (uint32_t i = 0; i < count; ++i) {
     if (!n[i].is_leaf) gidx[i] = next++;
-  auto leaf_ref = [&](uint32_t i, uint32_t& ref) {
-    int c = n[i].count, first = n[i].right_or_offset;
-    if (c <= 0 || c > bn::kMaxLeafCount) { err = std::string(what) + ": leaf item count out of range (1.." + std::to_string(bn::kMaxLeafCount) + ")"; return false; }
-    if (first < 0 || (uint32_t)first + (uint32_t)c > item_count || (uint32_t)first >= bn::kMaxLeafFirst) { err = std::string(what) + ": leaf item range out of bounds"; return false; }
-    ref = bn::kLeafBit | ((uint32_t)c << 24) | (uint32_t)first;
-    if (c > t.max_leaf) t.max_leaf = c;
-    return true;
-  };
-  auto child_ref = [&](uint32_t c, uint32_t& ref) {
-    if (n[c].is_leaf) return leaf_ref(c, ref);
-    ref = (uint32_t)gidx[c];
-    return true;
-  };
+    if (!finite3(n[i].bounds_min) || !finite3(n[i].bounds_max)) t.finite = false;
+  }
   out.resize(node_base + (size_t)next);
-  // depth via explicit stack (preorder array: left = i+1, right = RightChild)
+  // returns the ref for reference leaf i and the extra GNode levels it adds
+  auto leaf_ref = [&](uint32_t i, uint32_t& ref, int& extra) {
+    int c = n[i].count, first = n[i].right_or_offset;
+    extra = 0;
+    if (c <= 0) { err = std::string(what) + ": leaf item count out of range"; return false; }
+    if (first < 0 || (uint32_t)first + (uint32_t)c > item_count) { err = std::string(what) + ": leaf item range out of bounds"; return false; }
+    if (c > t.max_leaf) t.max_leaf = c;
+    if (!instances) {
+      if (c > bn::kMaxLeafCount || (uint32_t)first >= bn::kMaxLeafFirst) { err = std::string(what) + ": leaf too large for the 6-bit count / 24-bit offset encoding"; return false; }
+      ref = bn::kLeafBit | ((uint32_t)c << 24) | (uint32_t)first;
+      return true;
+    }
+    if ((uint32_t)first + (uint32_t)c > (1u << 30)) { err = "too many instances"; return false; }
+    if (c == 1) { ref = bn::kLeafBit | (uint32_t)first; return true; }
+    // chain of c-1 pseudo nodes, appended after the real interior nodes
+    const size_t base = out.size();
+    out.resize(base + (size_t)(c - 1));
+    for (int k = 0; k < c - 1; ++k) {
+      bn::GNode g;
+      const BnInstance& a = instances[first + k];
+      std::memcpy(g.lmin, a.bounds_min, 12); std::memcpy(g.lmax, a.bounds_max, 12);
+      g.left = bn::kLeafBit | (uint32_t)(first + k);
+      if (k == c - 2) {
+        const BnInstance& b = instances[first + k + 1];
+        std::memcpy(g.rmin, b.bounds_min, 12); std::memcpy(g.rmax, b.bounds_max, 12);
+        g.right = bn::kLeafBit | (uint32_t)(first + k + 1);
+      } else {
+        for (int d = 0; d < 3; ++d) { g.rmin[d] = -3.402823466e38f; g.rmax[d] = 3.402823466e38f; }
+        g.right = (uint32_t)(base - node_base + (size_t)k + 1);
+      }
+      g.axis = 3;
+      g.pad = 0;
+      out[base + (size_t)k] = g;
+    }
+    ref = (uint32_t)(base - node_base);
+    extra = c - 1;
+    return true;
+  };
+  auto child_ref = [&](uint32_t c, uint32_t& ref, int& extra) {
+    if (n[c].is_leaf) return leaf_ref(c, ref, extra);
+    ref = (uint32_t)gidx[c];
+    extra = 0;
+    return true;
+  };
+  // explicit stack (preorder array: left = i+1, right = RightChild)
   std::vector<std::pair<uint32_t, int>> stack{{0u, 1}};
   std::vector<char> seen(count, 0);
   while (!stack.empty()) {
@@ -59,7 +106,9 @@ bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_
     bn::GNode g;
     std::memcpy(g.lmin, n[l].bounds_min, 12); std::memcpy(g.lmax, n[l].bounds_max, 12);
     std::memcpy(g.rmin, n[r].bounds_min, 12); std::memcpy(g.rmax, n[r].bounds_max, 12);
-    if (!child_ref(l, g.left) || !child_ref((uint32_t)r, g.right)) return false;
+    int el = 0, er = 0;
+    if (!child_ref(l, g.left, el) || !child_ref((uint32_t)r, g.right, er)) return false;
+    if (depth + 1 + std::max(el, er) > t.depth) t.depth = depth + 1 + std::max(el, er);
     g.axis = (uint32_t)n[i].split_axis;
     g.pad = 0;
     out[node_base + (size_t)gidx[i]] = g;
@@ -69,8 +118,13 @@ bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_
   std::memcpy(t.tree.bmin, n[0].bounds_min, 12);
   std::memcpy(t.tree.bmax, n[0].bounds_max, 12);
   t.tree.node_base = node_base;
-  if (n[0].is_leaf) { if (!leaf_ref(0, t.tree.root)) return false; }
-  else t.tree.root = 0;
+  if (n[0].is_leaf) {
+    int extra = 0;
+    if (!leaf_ref(0, t.tree.root, extra)) return false;
+    t.depth = 1 + extra;
+  } else {
+    t.tree.root = 0;
+  }
   return true;
 }
 
@@ -90,8 +144,9 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
     return false;
   }
   TreeOut tl;
-  if (!build_tree(d.tlas_nodes, d.tlas_node_count, d.instance_count, 0, out.nodes, tl, err, "TLAS")) return false;
+  if (!build_tree(d.tlas_nodes, d.tlas_node_count, d.instance_count, 0, d.instances, out.nodes, tl, err, "TLAS")) return false;
   out.tlas = tl.tree;
+  out.all_finite = tl.finite;
   int max_blas_depth = 0;
   // meshes
   out.meshes.resize(d.mesh_count);
@@ -104,9 +159,9 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       return false;
     }
     TreeOut bt;
-    if (!build_tree(d.blas_nodes + mm.node_offset, mm.node_count, mm.tri_count, (uint32_t)out.nodes.size(), out.nodes, bt, err, "BLAS")) return false;
+    if (!build_tree(d.blas_nodes + mm.node_offset, mm.node_count, mm.tri_count, (uint32_t)out.nodes.size(), nullptr, out.nodes, bt, err, "BLAS")) return false;
     if (bt.depth > max_blas_depth) max_blas_depth = bt.depth;
-    if (bt.max_leaf > tl.max_leaf) {}
+    if (!bt.finite) out.all_finite = false;
     bn::GMesh& g = out.meshes[m];
     g.tree = bt.tree;
     g.tri_base = mm.tri_offset;
@@ -125,13 +180,16 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       }
     }
   }
-  out.max_stack = tl.depth + tl.max_leaf + max_blas_depth + 2;
+  for (size_t k = 0; k < (size_t)d.vertex_count * 3; ++k)
+    if (!std::isfinite(d.vertices[k])) { out.all_finite = false; break; }
+  out.max_stack = tl.depth + max_blas_depth + 2;
   if (out.max_stack > bn::kStackSize) {
     err = "scene needs a traversal stack of " + std::to_string(out.max_stack) + " entries (limit " + std::to_string(bn::kStackSize) + ")";
     return false;
   }
   // instances
   out.inst_head.resize(d.instance_count);
+  out.inst_trav.resize(d.instance_count);
   out.inst_w2o.resize(d.instance_count);
   out.inst_o2w.resize(d.instance_count);
   for (uint32_t i = 0; i < d.instance_count; ++i) {
@@ -145,13 +203,23 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
     h.light = in.light_id < 0 ? -1 : in.light_id;
     mat43(in.world_to_object, out.inst_w2o[i]);
     mat43(in.object_to_world, out.inst_o2w[i]);
+    bn::GInstTrav& tv = out.inst_trav[i];
+    std::memset(&tv, 0, sizeof tv);
+    std::memcpy(tv.w2o, out.inst_w2o[i].m, sizeof tv.w2o);
+    if (!finite3(in.bounds_min) || !finite3(in.bounds_max)) out.all_finite = false;
+    for (float v : tv.w2o) if (!std::isfinite(v)) out.all_finite = false;
     if (in.prim_kind == BN_PRIM_SPHERE) {
       if (in.prim_id >= d.sphere_count) { err = "instance sphere index out of range"; return false; }
       h.kind_prim = 0x80000000u | in.prim_id;
       h.light_pdf_area = d.sphere_radii[in.prim_id];
+      tv.is_sphere = 1;
+      tv.radius = d.sphere_radii[in.prim_id];
     } else if (in.prim_kind == BN_PRIM_MESH) {
       if (in.prim_id >= d.mesh_count) { err = "instance mesh index out of range"; return false; }
       h.kind_prim = in.prim_id;
+      const bn::GMesh& gm = out.meshes[in.prim_id];
+      std::memcpy(tv.bmin, gm.tree.bmin, 12); std::memcpy(tv.bmax, gm.tree.bmax, 12);
+      tv.root = gm.tree.root; tv.node_base = gm.tree.node_base; tv.tri_base = gm.tri_base;
       // MeshInstance.EvalPDF (Mesh.fs:300-304) for tag = 0:
       // Table[0].pdf / SurfaceArea(Transform(triangle 0, ObjectToWorld))
       const BnMesh& mm = d.meshes[in.prim_id];

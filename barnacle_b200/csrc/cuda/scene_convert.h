@@ -11,6 +11,7 @@ namespace bnconv {
 struct ConvertedScene {
   std::vector<bn::GNode> nodes;
   bn::GTree tlas;
+  std::vector<bn::GInstTrav> inst_trav;
   std::vector<bn::GInstHead> inst_head;
   std::vector<bn::GMat43> inst_w2o, inst_o2w;
   std::vector<bn::GMesh> meshes;
@@ -22,6 +23,7 @@ struct ConvertedScene {
   std::vector<uint32_t> light_inst;
   bn::GCamera cam;
   int max_stack = 0;
+  bool all_finite = true;
 };
 
 // Validates the description (indices in range, well-formed preorder trees, leaf

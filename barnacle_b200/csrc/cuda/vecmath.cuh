@@ -98,20 +98,40 @@ struct Slab {
   float tmin;  // Max(1e-3, Max(lo.x, Max(lo.y, lo.z)))
   float thi;   // Min(hi.x, Min(hi.y, hi.z))
 };
+// FAST = false: the reference's operations one for one (minps/maxps selects,
+// NaN-propagating Math.Max/Min).
+// FAST = true: plain fmin/fmax.  Bit-identical to the exact form whenever no lane
+// can be NaN, i.e. every component of 1/d is finite and non-zero and the box and
+// origin are finite (then (p - o) * inv is never 0 * inf; sign-of-zero differences
+// between minps and fmin cannot survive the Max with 1e-3 or change a comparison).
+// The caller picks FAST per ray and per space with slab_fast_ok(); rays with a
+// zero / denormal / infinite direction component take the exact path.
+template <bool FAST>
 BN_DEV Slab slab(float3 pmin, float3 pmax, float3 o, float3 inv) {
-  float3 t0 = (pmin - o) * inv;
-  float3 t1 = (pmax - o) * inv;
-  float3 lo = min_native(t0, t1);
-  float3 hi = max_native(t0, t1);
+  const float3 t0 = (pmin - o) * inv;
+  const float3 t1 = (pmax - o) * inv;
   Slab s;
-  s.tmin = net_max(1e-3f, net_max(lo.x, net_max(lo.y, lo.z)));
-  s.thi = net_min(hi.x, net_min(hi.y, hi.z));
+  if (FAST) {
+    s.tmin = fmaxf(fmaxf(1e-3f, fminf(t0.x, t1.x)), fmaxf(fminf(t0.y, t1.y), fminf(t0.z, t1.z)));
+    s.thi = fminf(fmaxf(t0.x, t1.x), fminf(fmaxf(t0.y, t1.y), fmaxf(t0.z, t1.z)));
+  } else {
+    const float3 lo = min_native(t0, t1);
+    const float3 hi = max_native(t0, t1);
+    s.tmin = net_max(1e-3f, net_max(lo.x, net_max(lo.y, lo.z)));
+    s.thi = net_min(hi.x, net_min(hi.y, hi.z));
+  }
   return s;
+}
+BN_DEV bool slab_fast_ok(float3 o, float3 inv) {
+  const float big = 3.0e38f;
+  return fabsf(inv.x) < big && fabsf(inv.y) < big && fabsf(inv.z) < big && inv.x != 0.f && inv.y != 0.f && inv.z != 0.f &&
+         fabsf(o.x) < 1.0e37f && fabsf(o.y) < 1.0e37f && fabsf(o.z) < 1.0e37f;
 }
 // ... and the part that does: tMin <= Min(t, thi).  For non-NaN t this equals
 // (tmin <= t) && (tmin <= thi), which is what lets a deferred child be
 // re-checked against the CURRENT t at pop time exactly as the reference does.
-BN_DEV bool slab_pass(const Slab& s, float t) { return s.tmin <= net_min(t, s.thi); }
+template <bool FAST>
+BN_DEV bool slab_pass(const Slab& s, float t) { return FAST ? (s.tmin <= fminf(t, s.thi)) : (s.tmin <= net_min(t, s.thi)); }
 
 // OrthonormalBasis (Primitive.fs:9-40)
 struct Onb { float3 n, t, b; };

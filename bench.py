@@ -49,9 +49,15 @@ MAX_DEPTH, RR_DEPTH = 8, 5
 B_NODE, B_TRI, B_INST, B_IO_EXTEND, B_IO_SHADOW = 32, 48, 152, 48, 32
 
 
-def algorithmic_bytes_per_ray(c: dict, io: int) -> float:
+def algorithmic_bytes_per_ray(c: dict, io: int, cap: bool = False) -> float:
+    """32 B per node popped + 48 B per leaf triangle fetched + the instance
+    record + ray/hit I/O, all in the REFERENCE layout and visiting order.  The instance
+    term is the exact split the oracle counts (24 B bounds per instance visited, + 64 B
+    WorldToObject when its AABB passes, + 64 B ObjectToWorld on a committed hit);
+    cap=True charges the full 152 B per visit instead (the survey's upper bound)."""
     rays = max(c["rays"], 1)
-    return (B_NODE * (c["tlas_nodes"] + c["blas_nodes"]) + B_TRI * c["tris_fetched"] + B_INST * c["inst_visited"]) / rays + io
+    inst = B_INST * c["inst_visited"] if cap else 24 * c["inst_visited"] + 64 * c["inst_box_pass"] + 64 * c["inst_committed"]
+    return (B_NODE * (c["tlas_nodes"] + c["blas_nodes"]) + B_TRI * c["tris_fetched"] + inst) / rays + io
 
 
 class ClockSampler:
@@ -286,12 +292,13 @@ def main():
         achieved = tot["extend"] * b_ext / ext_s / 1e9 if ext_s > 0 else None
         roofline = {"bound": "hbm", "kernel": "k_extend (closest-hit TLAS+BLAS traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_ray": b_ext, "rays_per_s": tot["extend"] / ext_s if ext_s > 0 else None,
+                    "algorithmic_bytes_per_ray": b_ext, "algorithmic_bytes_per_ray_cap152": algorithmic_bytes_per_ray(cst["extend_counters"], B_IO_EXTEND, cap=True),
+                    "rays_per_launch": tot["extend"] / max(1, launches_total // 26 * 8), "rays_per_s": tot["extend"] / ext_s if ext_s > 0 else None,
                     "kernel_share_of_step": tot["extend_ms"] / tot["render_ms"] if tot["render_ms"] else None,
                     "shadow": {"algorithmic_bytes_per_ray": b_sh, "achieved": (tot["shadow"] * b_sh / (tot["shadow_ms"] * 1e-3) / 1e9) if tot["shadow_ms"] else None,
                                "rays_per_s": tot["shadow"] / (tot["shadow_ms"] * 1e-3) if tot["shadow_ms"] else None},
                     "rank0_class_ms_per_step": {k: tot[k + "_ms"] / args.steps for k in ("extend", "shade", "shadow", "other")},
-                    "note": "bytes/ray = 32*N_node + 48*N_tri + 152*N_inst + 48 I/O in the REFERENCE layout (SURVEY 8d), counted by the instrumented oracle "
+                    "note": "bytes/ray = 32*N_node + 48*N_tri + (24*N_inst_visited + 64*N_inst_boxpass + 64*N_inst_committed) + 48 I/O in the REFERENCE layout (SURVEY 8d), counted by the instrumented oracle "
                             f"on {cw}x{ch}x2spp of this scene; scene data is L2-resident, so this is an algorithmic-traffic rate against the HBM copy peak"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
