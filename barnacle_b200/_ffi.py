@@ -19,6 +19,7 @@ BN_MAT_LAMBERTIAN, BN_MAT_MIRROR, BN_MAT_DIELECTRIC, BN_MAT_PBR = 0, 1, 2, 3
 BN_CAM_PINHOLE, BN_CAM_THIN_LENS = 0, 1
 BN_RENDER_TRACE_NULL_SHADOW = 1
 BN_RENDER_PROFILE = 2
+BN_RENDER_FORCE_EXACT = 4
 
 
 class BnBVHNode(C.Structure):

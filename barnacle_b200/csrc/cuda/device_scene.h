@@ -8,16 +8,16 @@
 namespace bn {
 
 // Child reference encoding (GNode.left/right, traversal stack entries)
-//   bit31 = 0 : interior node, bits 0..29 = GNode index within the current tree
+//   bit31 = 0 : interior node, bits 0..29 = ABSOLUTE GNode index (scene-wide array)
 //   bit31 = 1 : leaf
-//        BLAS: bits 24..29 = triangle count (<= 63), bits 0..23 = first triangle
+//        BLAS: bits 27..29 = triangle count (<= 7), bits 0..26 = ABSOLUTE first triangle
 //        TLAS: bits 0..29  = instance slot (every TLAS leaf is ONE instance, see
 //              scene_convert.cpp: a reference leaf of k instances becomes a chain
 //              of k-1 order-preserving pseudo nodes)
 // During traversal TLAS-level refs additionally carry kTlasBit (bit 30) so a pop
 // knows which space the ray is in.  GNode.axis == 3 means "always left first".
 constexpr uint32_t kLeafBit = 0x80000000u;
-constexpr uint32_t kMaxLeafFirst = 1u << 24;
+constexpr uint32_t kMaxLeafFirst = 1u << 27;
 
 // Interior node: BOTH children's boxes in the parent (one 64-B fetch per
 // interior visit instead of two dependent 32-B fetches of BVHNode).  Topology

@@ -112,27 +112,37 @@ __global__ void __launch_bounds__(kBlock) k_raygen(DScene sc, WaveParams wp, flo
 }
 
 // ---- extend: closest hit for every live path ----------------------------------------
+struct DeferList {  // rays that need the exact traversal (fix-up kernel)
+  int* count;
+  int* list;
+  BN_DEV void push(int i) const { list[atomicAdd(count, 1)] = i; }
+};
 struct ExtendIO {
   const float4* __restrict__ s0;
   const float4* __restrict__ s1;
   float4* __restrict__ hits;
-  int n;
+  const int* __restrict__ n_ptr;
   int* cur;
-  BN_DEV int count() const { return n; }
+  DeferList deferred;
+  BN_DEV int count() const { return *n_ptr; }
   BN_DEV int* cursor() const { return cur; }
   BN_DEV void load(int i, float3& o, float3& d, float& t) const {
     const float4 a = s0[i], b = s1[i];
     o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
     t = CUDART_INF_F;  // PathTracing.fs:25
   }
-  BN_DEV void store(int i, bool, float t, int inst, int prim, float, float) const {
-    hits[i] = make_float4(t, __int_as_float(inst), __int_as_float(prim), 0.f);
+  BN_DEV void store(int i, const TraceResult& r) const {
+    hits[i] = make_float4(r.t, __int_as_float(r.inst), __int_as_float(r.prim), 0.f);
   }
+  BN_DEV void defer(int i) const { deferred.push(i); }
 };
-__global__ void __launch_bounds__(kBlock) k_extend(DScene sc, const float4* __restrict__ s0, const float4* __restrict__ s1,
-                                                   float4* __restrict__ hits, const int* __restrict__ n_ptr, int* cursor) {
-  ExtendIO io{s0, s1, hits, *n_ptr, cursor};
-  traverse_persistent<false>(sc, io);
+template <bool ANY, class IO>
+__global__ void __launch_bounds__(kBlock, 8) k_traverse(DScene sc, IO io) {
+  traverse_persistent<ANY>(sc, io);
+}
+template <bool ANY, class IO>
+__global__ void __launch_bounds__(kBlock) k_traverse_fixup(DScene sc, IO io) {
+  traverse_deferred<ANY>(sc, io, io.deferred.list, *io.deferred.count);
 }
 
 // ---- shade: one iteration of Li's loop body (PathTracing.fs:30-79) --------------------
@@ -178,10 +188,8 @@ __global__ void __launch_bounds__(kBlock) k_shade(DScene sc, WaveParams wp, int 
           nobj = normalize(pobj);
           if (prim == 0 && dot(nobj, od) > 0.f) nobj = -nobj;
         } else {          // Mesh.fs:76-78
-          const GMesh* mesh = sc.meshes + kind_prim;
-          const float4 m2 = __ldg(reinterpret_cast<const float4*>(mesh) + 2);
           float3 p0, p1, p2;
-          load_tri(sc.tris + __float_as_uint(m2.x) + prim, p0, p1, p2);
+          load_tri(sc.tris + prim, p0, p1, p2);  // prim is the scene-wide triangle index
           nobj = normalize(cross(p1 - p0, p2 - p0));
         }
         // LocalGeometry.Transform (Primitive.fs:57-58)
@@ -268,29 +276,26 @@ struct ShadowIO {
   const float4* __restrict__ q2;
   const float4* __restrict__ q3;
   float4* __restrict__ rad;
-  int n;
+  const int* __restrict__ n_ptr;
   int* cur;
-  BN_DEV int count() const { return n; }
+  DeferList deferred;
+  BN_DEV int count() const { return *n_ptr; }
   BN_DEV int* cursor() const { return cur; }
   BN_DEV void load(int i, float3& o, float3& d, float& t) const {
     const float4 a = q0[i], b = q1[i];
     o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
     t = b.z;
   }
-  BN_DEV void store(int i, bool occluded, float, int, int, float, float) const {
-    if (occluded) return;
+  BN_DEV void store(int i, const TraceResult& r) const {
+    if (r.hit) return;  // occluded
     const float4 b = q1[i], c = q2[i], e = q3[i];
     const int pid = __float_as_int(b.w);
     const float4 L4 = rad[pid];
     const float3 L = vfma(f3(c.x, c.y, c.z), f3(c.w, e.x, e.y), f3(L4.x, L4.y, L4.z));
     rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
   }
+  BN_DEV void defer(int i) const { deferred.push(i); }
 };
-__global__ void __launch_bounds__(kBlock) k_shadow(DScene sc, const float4* __restrict__ q0, const float4* __restrict__ q1, const float4* __restrict__ q2,
-                                                   const float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr, int* cursor) {
-  ShadowIO io{q0, q1, q2, q3, rad, *n_ptr, cursor};
-  traverse_persistent<true>(sc, io);
-}
 
 // ---- accumulate: accum = fma(1/spp, radiance, accum); Film.SetPixel -------------------
 // (Integrator.fs:41-44, Film.fs:41-46).  One thread per pixel walks its samples in
@@ -336,20 +341,27 @@ struct TraceIO {
   BnHit* __restrict__ hits;
   int n;
   int* cur;
+  DeferList deferred;
   BN_DEV int count() const { return n; }
   BN_DEV int* cursor() const { return cur; }
+  BN_DEV void defer(int i) const { deferred.push(i); }
   BN_DEV void load(int i, float3& o, float3& d, float& t) const {
     const BnRay r = rays[i];
     o = f3(r.origin[0], r.origin[1], r.origin[2]); d = f3(r.direction[0], r.direction[1], r.direction[2]);
     t = r.tmax;
   }
-  BN_DEV void store(int i, bool hit, float t, int inst, int prim, float u, float v) const {
+  BN_DEV void store(int i, const TraceResult& res) const {
     BnHit out;
+    const bool hit = res.hit;
+    const float t = res.t;
+    const int inst = res.inst;
     if (ANY) {
       out.t = 0.f; out.u = 0.f; out.v = 0.f; out.instance = hit ? 1 : 0; out.primitive = 0;
     } else {
-      out.t = t; out.u = u; out.v = v; out.instance = inst; out.primitive = prim;
+      out.t = t; out.u = res.u; out.v = res.v; out.instance = inst; out.primitive = res.prim;
       if (hit) {
+        // BnHit.primitive is the BLAS-order index WITHIN the mesh; the kernel carries scene-wide indices
+        out.primitive = res.prim - (int)sc.inst_trav[inst].tri_base;
         const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.inst_head + inst));
         if (__float_as_uint(h0.w) & 0x80000000u) {  // sphere uv (Sphere.fs:55-56), libdevice atan2/acos
           const BnRay r = rays[i];
@@ -365,12 +377,6 @@ struct TraceIO {
     hits[i] = out;
   }
 };
-template <bool ANY>
-__global__ void __launch_bounds__(kBlock) k_trace(DScene sc, const BnRay* __restrict__ rays, int n, BnHit* __restrict__ hits, int* cursor) {
-  TraceIO<ANY> io{sc, rays, hits, n, cursor};
-  traverse_persistent<ANY>(sc, io);
-}
-
 }  // namespace bn
 
 // =================================================================================
@@ -389,6 +395,7 @@ struct BnScene {
   float4* hits = nullptr;
   float4* shq = nullptr;                  // 4 planes
   float4* rad = nullptr;
+  int* defer_list = nullptr;              // rays deferred to the exact fix-up kernel (cap entries)
   int* counters = nullptr;
   size_t counters_len = 0;
   unsigned long long* shadow_ref = nullptr;
@@ -430,7 +437,7 @@ size_t wave_capacity_paths() {
 
 int ensure_wave_buffers(BnScene* s, size_t cap) {
   if (s->cap >= cap) return BN_OK;
-  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad})
+  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list})
     if (p) cudaFree(p);
   s->cap = 0;
   BN_CUDA(cudaMalloc((void**)&s->state[0], cap * 3 * sizeof(float4)));
@@ -438,6 +445,7 @@ int ensure_wave_buffers(BnScene* s, size_t cap) {
   BN_CUDA(cudaMalloc((void**)&s->hits, cap * sizeof(float4)));
   BN_CUDA(cudaMalloc((void**)&s->shq, cap * 4 * sizeof(float4)));
   BN_CUDA(cudaMalloc((void**)&s->rad, cap * sizeof(float4)));
+  BN_CUDA(cudaMalloc((void**)&s->defer_list, cap * sizeof(int)));
   s->cap = cap;
   return BN_OK;
 }
@@ -482,9 +490,9 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     const long long n_block_chunks = (total_blocks + blocks_per_wave - 1) / blocks_per_wave;
     const long long n_sample_chunks = (ns + samples_per_wave - 1) / samples_per_wave;
     const long long n_waves = n_block_chunks * n_sample_chunks;
-    // per wave: [0] n_active(bounce 0..maxDepth) | n_shadow(bounce) | cursors 3 per bounce
+    // per wave: n_active(bounce 0..maxDepth) | n_shadow(bounce) | cursors 3 per bounce | deferred counts 2 per bounce
     const int D = p->max_depth;
-    const size_t per_wave = (size_t)(D + 1) + D + 3 * (size_t)D;
+    const size_t per_wave = (size_t)(D + 1) + D + 3 * (size_t)D + 2 * (size_t)D;
     const size_t need = per_wave * (size_t)n_waves;
     if (s->counters_len < need) {
       if (s->counters) cudaFree(s->counters);
@@ -495,6 +503,8 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     BN_CUDA(cudaMemsetAsync(s->counters, 0, need * sizeof(int), stream));
     BN_CUDA(cudaMemsetAsync(s->shadow_ref, 0, sizeof(unsigned long long), stream));
     const int grid = s->num_sms * 8;
+    DScene dsc = s->d;
+    if (p->flags & BN_RENDER_FORCE_EXACT) dsc.all_finite = 0u;  // every ray is deferred to the exact fix-up kernel
     // BN_RENDER_PROFILE: bracket every launch with events on the launching stream
     const bool profile = (p->flags & BN_RENDER_PROFILE) != 0 && stats != nullptr;
     std::vector<int> ev_class;  // 0 extend, 1 shade, 2 shadow, 3 other
@@ -533,6 +543,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         int* n_active = base;
         int* n_shadow = base + (D + 1);
         int* cursors = base + (D + 1) + D;
+        int* n_defer = cursors + 3 * D;
         const size_t cp = s->cap;
         float4* A = s->state[0];
         float4* B = s->state[1];
@@ -542,7 +553,9 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         ++launches;
         for (int b = 0; b < D; ++b) {
           prof_begin(0);
-          k_extend<<<grid, kBlock, 0, stream>>>(s->d, A, A + cp, s->hits, n_active + b, cursors + 3 * b);
+          const ExtendIO eio{A, A + cp, s->hits, n_active + b, cursors + 3 * b, DeferList{n_defer + 2 * b, s->defer_list}};
+          k_traverse<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
+          k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
           prof_end();
           prof_begin(1);
           k_shade<<<grid, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
@@ -550,9 +563,11 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
                                                cursors + 3 * b + 1, s->shadow_ref);
           prof_end();
           prof_begin(2);
-          k_shadow<<<grid, kBlock, 0, stream>>>(s->d, s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b, cursors + 3 * b + 2);
+          const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b, cursors + 3 * b + 2, DeferList{n_defer + 2 * b + 1, s->defer_list}};
+          k_traverse<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
+          k_traverse_fixup<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
           prof_end();
-          launches += 3;
+          launches += 5;
           std::swap(A, B);
         }
         prof_begin(3);
@@ -652,7 +667,7 @@ void bn_scene_destroy(BnScene* s) {
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
-  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->counters, (void*)s->shadow_ref, (void*)s->film})
+  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list, (void*)s->counters, (void*)s->shadow_ref, (void*)s->film})
     if (p) cudaFree(p);
   delete s;
 }
@@ -703,11 +718,14 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
   if (s->poisoned) { bnhost::set_error("scene is unusable after an earlier CUDA error"); return BN_ERR_CUDA; }
   BN_CUDA(cudaSetDevice(s->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  const uint64_t chunk = 1ull << 30;
+  const uint64_t chunk = 1ull << 28;
   const int n_chunks = (int)((n + chunk - 1) / chunk);
-  int* cursors = nullptr;
-  BN_CUDA(cudaMalloc((void**)&cursors, sizeof(int) * (size_t)std::max(n_chunks, 1)));
-  BN_CUDA(cudaMemsetAsync(cursors, 0, sizeof(int) * (size_t)std::max(n_chunks, 1), stream));
+  // per chunk: cursor, deferred count; one deferred list shared by the (stream-ordered) chunks
+  int* ctr = nullptr;
+  int* dlist = nullptr;
+  BN_CUDA(cudaMalloc((void**)&ctr, sizeof(int) * 2 * (size_t)std::max(n_chunks, 1)));
+  BN_CUDA(cudaMalloc((void**)&dlist, sizeof(int) * (size_t)std::max<uint64_t>(std::min<uint64_t>(chunk, n), 1)));
+  BN_CUDA(cudaMemsetAsync(ctr, 0, sizeof(int) * 2 * (size_t)std::max(n_chunks, 1), stream));
   cudaEvent_t e0, e1;
   BN_CUDA(cudaEventCreate(&e0));
   BN_CUDA(cudaEventCreate(&e1));
@@ -717,8 +735,15 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
     const BnRay* r = static_cast<const BnRay*>(d_rays) + (uint64_t)c * chunk;
     BnHit* h = static_cast<BnHit*>(d_hits) + (uint64_t)c * chunk;
     const int m = (int)std::min<uint64_t>(chunk, n - (uint64_t)c * chunk);
-    if (any_hit) k_trace<true><<<grid, kBlock, 0, stream>>>(s->d, r, m, h, cursors + c);
-    else k_trace<false><<<grid, kBlock, 0, stream>>>(s->d, r, m, h, cursors + c);
+    if (any_hit) {
+      const TraceIO<true> io{s->d, r, h, m, ctr + 2 * c, DeferList{ctr + 2 * c + 1, dlist}};
+      k_traverse<true, TraceIO<true>><<<grid, kBlock, 0, stream>>>(s->d, io);
+      k_traverse_fixup<true, TraceIO<true>><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
+    } else {
+      const TraceIO<false> io{s->d, r, h, m, ctr + 2 * c, DeferList{ctr + 2 * c + 1, dlist}};
+      k_traverse<false, TraceIO<false>><<<grid, kBlock, 0, stream>>>(s->d, io);
+      k_traverse_fixup<false, TraceIO<false>><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
+    }
   }
   BN_CUDA(cudaEventRecord(e1, stream));
   cudaError_t e = cudaStreamSynchronize(stream);
@@ -727,7 +752,8 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
   if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  cudaFree(cursors);
+  cudaFree(ctr);
+  cudaFree(dlist);
   if (e != cudaSuccess) { s->poisoned = true; cuda_ok(e, "bn_trace"); return BN_ERR_CUDA; }
   if (ms) *ms = t;
   return BN_OK;

@@ -35,7 +35,7 @@ bool finite3(const float* v) { return std::isfinite(v[0]) && std::isfinite(v[1])
 // which visits the instances in slot order, each against the then-current t —
 // exactly the loop at Aggregate/BVH.fs:49-50 (a link fails only when t < 1e-3, and
 // then every instance test would fail too because tMin >= 1e-3).
-bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_t node_base, const BnInstance* instances,
+bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_t node_base, uint32_t item_base, const BnInstance* instances,
                 std::vector<bn::GNode>& out, TreeOut& t, std::string& err, const char* what) {
   if (count == 0) { err = std::string(what) + ": empty BVH"; return false; }
   std::vector<int> gidx(count, -1);
@@ -53,8 +53,9 @@ bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_
     if (first < 0 || (uint32_t)first + (uint32_t)c > item_count) { err = std::string(what) + ": leaf item range out of bounds"; return false; }
     if (c > t.max_leaf) t.max_leaf = c;
     if (!instances) {
-      if (c > bn::kMaxLeafCount || (uint32_t)first >= bn::kMaxLeafFirst) { err = std::string(what) + ": leaf too large for the 6-bit count / 24-bit offset encoding"; return false; }
-      ref = bn::kLeafBit | ((uint32_t)c << 24) | (uint32_t)first;
+      // refs are ABSOLUTE (scene-wide triangle index): 3-bit count, 27-bit first
+      if (c > bn::kMaxLeafCount || (uint64_t)item_base + (uint64_t)first >= bn::kMaxLeafFirst) { err = std::string(what) + ": leaf too large for the 3-bit count / 27-bit offset encoding"; return false; }
+      ref = bn::kLeafBit | ((uint32_t)c << 27) | (item_base + (uint32_t)first);
       return true;
     }
     if ((uint32_t)first + (uint32_t)c > (1u << 30)) { err = "too many instances"; return false; }
@@ -73,19 +74,19 @@ bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_
         g.right = bn::kLeafBit | (uint32_t)(first + k + 1);
       } else {
         for (int d = 0; d < 3; ++d) { g.rmin[d] = -3.402823466e38f; g.rmax[d] = 3.402823466e38f; }
-        g.right = (uint32_t)(base - node_base + (size_t)k + 1);
+        g.right = (uint32_t)(base + (size_t)k + 1);
       }
       g.axis = 3;
       g.pad = 0;
       out[base + (size_t)k] = g;
     }
-    ref = (uint32_t)(base - node_base);
+    ref = (uint32_t)base;
     extra = c - 1;
     return true;
   };
   auto child_ref = [&](uint32_t c, uint32_t& ref, int& extra) {
     if (n[c].is_leaf) return leaf_ref(c, ref, extra);
-    ref = (uint32_t)gidx[c];
+    ref = node_base + (uint32_t)gidx[c];  // ABSOLUTE GNode index
     extra = 0;
     return true;
   };
@@ -123,8 +124,9 @@ bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_
     if (!leaf_ref(0, t.tree.root, extra)) return false;
     t.depth = 1 + extra;
   } else {
-    t.tree.root = 0;
+    t.tree.root = node_base;
   }
+  if (out.size() >= (1u << 30)) { err = "too many BVH nodes"; return false; }
   return true;
 }
 
@@ -144,7 +146,7 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
     return false;
   }
   TreeOut tl;
-  if (!build_tree(d.tlas_nodes, d.tlas_node_count, d.instance_count, 0, d.instances, out.nodes, tl, err, "TLAS")) return false;
+  if (!build_tree(d.tlas_nodes, d.tlas_node_count, d.instance_count, 0, 0, d.instances, out.nodes, tl, err, "TLAS")) return false;
   out.tlas = tl.tree;
   out.all_finite = tl.finite;
   int max_blas_depth = 0;
@@ -159,7 +161,7 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       return false;
     }
     TreeOut bt;
-    if (!build_tree(d.blas_nodes + mm.node_offset, mm.node_count, mm.tri_count, (uint32_t)out.nodes.size(), nullptr, out.nodes, bt, err, "BLAS")) return false;
+    if (!build_tree(d.blas_nodes + mm.node_offset, mm.node_count, mm.tri_count, (uint32_t)out.nodes.size(), mm.tri_offset, nullptr, out.nodes, bt, err, "BLAS")) return false;
     if (bt.depth > max_blas_depth) max_blas_depth = bt.depth;
     if (!bt.finite) out.all_finite = false;
     bn::GMesh& g = out.meshes[m];

@@ -22,6 +22,13 @@
 //   T  triangles of the held BLAS leaf, one triangle per step across the lanes
 // Lanes whose ray is finished are refilled from the global queue (one
 // warp-aggregated atomic) as soon as enough of them are idle.
+//
+// The phases run the FAST slab form (vecmath.cuh), which is bit-identical to the
+// reference's for every ray whose 1/d has only finite non-zero components.  A ray
+// that is not (zero / denormal direction component, in world or in some object
+// space) is appended to a deferred list and re-traced from scratch by the
+// companion fix-up kernel with trace_exact(), a plain per-lane loop that spells
+// out the minps/maxps + NaN-propagating Math.Max/Min sequence.
 #pragma once
 #include "device_scene.h"
 #include "traverse_limits.h"
@@ -31,17 +38,10 @@ namespace bn {
 
 constexpr uint32_t kTlasBit = 0x40000000u;
 constexpr uint32_t kIndexMask = 0x3FFFFFFFu;
-constexpr uint32_t kFirstMask = 0x00FFFFFFu;
+constexpr uint32_t kFirstMask = 0x07FFFFFFu;
 constexpr uint32_t kNone = 0xFFFFFFFFu;  // "stack empty": a leaf ref that no scene can produce
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kRefillMin = 8;            // refill when at least this many lanes are idle
-
-struct HitRec {
-  float t;
-  int inst;   // TLAS-order instance slot, -1 = miss
-  int prim;   // BLAS-order triangle; spheres: 0 = near root (t0), 1 = far root (t1)
-  float u, v; // barycentrics (triangles only)
-};
 
 BN_DEV uint32_t fbits(float f) { return __float_as_uint(f); }
 
@@ -81,63 +81,153 @@ BN_DEV int sphere_test(float radius, float3 o, float3 d, float t, float& tp) {
   return 0;
 }
 
-// Per-lane traversal state of the persistent loop.
-struct Lane {
-  float3 wo, wd;          // world-space ray
-  float3 o, d, inv;       // ray in the CURRENT space
-  float t;                // closest distance so far (ANY: the fixed tmax)
-  int h_inst, h_prim;
-  float h_u, h_v;
-  uint32_t cur;           // ref being processed (kNone: nothing left)
-  int sp;
-  int cur_inst;
-  int index;              // queue slot of this ray
-  const GNode* nodes;
-  const GTri* tris;
-  bool in_obj, fast, wfast, active;
+// bit a set iff d[a] > 0; bit 3 always set (GNode.axis == 3: "always left first")
+BN_DEV uint32_t dir_signs(float3 d) { return (d.x > 0.f ? 1u : 0u) | (d.y > 0.f ? 2u : 0u) | (d.z > 0.f ? 4u : 0u) | 8u; }
+
+struct TraceResult {
+  bool hit;
+  float t;
+  int inst, prim;  // prim: ABSOLUTE triangle index; spheres: 0 = near root (t0), 1 = far root (t1)
+  float u, v;
 };
 
+// ---------------------------------------------------------------------------------
+// Exact per-lane traversal (slow path, fix-up kernel).  Same visiting order, the
+// reference's slab operations spelled out (slab<false>).
+// ---------------------------------------------------------------------------------
+template <bool ANY>
+BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, float t, TraceResult& res) {
+  uint2 stk[kStackSize];
+  int sp = 0;
+  const float3 winv = rcp3(wd);
+  float3 o = wo, d = wd, inv = winv;
+  uint32_t signs = dir_signs(wd);
+  bool in_obj = false;
+  int cur_inst = -1;
+  res.hit = false; res.t = t; res.inst = -1; res.prim = -1; res.u = 0.f; res.v = 0.f;
+  if (!slab_pass<false>(slab<false>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv), t)) return;
+  uint32_t cur = sc.tlas.root | kTlasBit;
+  for (;;) {
+    if ((cur & kTlasBit) && in_obj) { o = wo; d = wd; inv = winv; signs = dir_signs(wd); in_obj = false; }
+    if (!(cur & kLeafBit)) {
+      const float4* np = reinterpret_cast<const float4*>(sc.nodes + (cur & kIndexMask));
+      const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+      const Slab sl = slab<false>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
+      const Slab sr = slab<false>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
+      const bool pl = slab_pass<false>(sl, t), pr = slab_pass<false>(sr, t);
+      const uint32_t level = cur & kTlasBit;
+      const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
+      const bool left_first = ((signs >> fbits(n3.z)) & 1u) != 0u;
+      const uint32_t nref = left_first ? left : right, fref = left_first ? right : left;
+      const bool pn = left_first ? pl : pr, pf = left_first ? pr : pl;
+      if (pn) {
+        cur = nref;
+        if (pf) { stk[sp] = make_uint2(fref, __float_as_uint(left_first ? sr.tmin : sl.tmin)); ++sp; }
+        continue;
+      }
+      if (pf) { cur = fref; continue; }
+    } else if (cur & kTlasBit) {
+      const uint32_t slot = cur & kIndexMask;
+      const float4* ip = reinterpret_cast<const float4*>(sc.inst_trav + slot);
+      const Mat43 M = load_mat43(ip);
+      const float4 m0 = __ldg(ip + 3), m1 = __ldg(ip + 4), m2 = __ldg(ip + 5);
+      const float3 oo = transform_point(wo, M), od = transform_dir(wd, M);
+      if (fbits(m2.y)) {
+        float tp;
+        const int root = sphere_test(m2.z, oo, od, t, tp);
+        if (root) {
+          res.hit = true; res.inst = (int)slot; res.prim = root - 1; res.u = 0.f; res.v = 0.f;
+          if (ANY) return;
+          t = tp; res.t = tp;
+        }
+      } else {
+        o = oo; d = od; inv = rcp3(od); signs = dir_signs(od);
+        in_obj = true;
+        cur_inst = (int)slot;
+        if (slab_pass<false>(slab<false>(f3(m0.x, m0.y, m0.z), f3(m1.x, m1.y, m1.z), o, inv), t)) { cur = fbits(m0.w); continue; }
+      }
+    } else {
+      const uint32_t count = (cur >> 27) & 7u, first = cur & kFirstMask;
+      for (uint32_t k = 0; k < count; ++k) {
+        const float4* tp4 = reinterpret_cast<const float4*>(sc.tris + first + k);
+        const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
+        const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
+        const float3 lo = min_native(min_native(p0, p1), p2), hi = max_native(max_native(p0, p1), p2);
+        if (!slab_pass<false>(slab<false>(lo, hi, o, inv), t)) continue;
+        float tp, u, v;
+        if (tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
+          res.hit = true; res.inst = cur_inst; res.prim = (int)(first + k); res.u = u; res.v = v;
+          if (ANY) return;
+          t = tp; res.t = tp;
+        }
+      }
+    }
+    for (;;) {
+      if (sp == 0) return;
+      --sp;
+      cur = stk[sp].x;
+      if (ANY || __uint_as_float(stk[sp].y) <= t) break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Persistent warp-synchronous traversal (fast path).
 // IO concept:  int count() ; int* cursor() ;
 //              void load(int i, float3& o, float3& d, float& tmax) ;
-//              void store(int i, bool hit, float t, int inst, int prim, float u, float v)
+//              void store(int i, const TraceResult&) ;
+//              void defer(int i)      // ray i needs the exact path (fix-up kernel)
+// ---------------------------------------------------------------------------------
 template <bool ANY, class IO>
 BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
   uint2 stk[kStackSize];  // (ref, entry distance bits)
-  Lane L;
-  L.active = false;
-  L.cur = kNone;
-  L.sp = 0;
+  // per-lane state
+  float3 wo, wd;          // world-space ray
+  float3 o, d, inv;       // ray in the CURRENT space
+  float t = 0.f;          // closest distance so far (ANY: the fixed tmax)
+  int h_inst = -1, h_prim = -1;
+  float h_u = 0.f, h_v = 0.f;
+  uint32_t cur = kNone;   // ref being processed
+  uint32_t signs = 8u;    // dir_signs of the current-space direction
+  int sp = 0;
+  int cur_inst = -1;
+  int index = 0;          // queue slot of this ray
+  bool in_obj = false, active = false;
+  wo = wd = o = d = inv = splat(0.f);
+
   const int n = io.count();
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   bool exhausted = false;
   const bool scene_fast = sc.all_finite != 0u;
+  const float4* const node_base = reinterpret_cast<const float4*>(sc.nodes);
+  const float4* const tri_base = reinterpret_cast<const float4*>(sc.tris);
 
-  // pops the next entry whose stored entry distance still passes; kNone if empty
+  auto finish = [&]() {
+    TraceResult r;
+    r.hit = h_inst >= 0; r.t = t; r.inst = h_inst; r.prim = h_prim; r.u = h_u; r.v = h_v;
+    io.store(index, r);
+    active = false;
+    cur = kNone;
+  };
+  // pops the next entry whose stored entry distance still passes; finishes the ray if none
   auto pop = [&]() {
     for (;;) {
-      if (L.sp == 0) { L.cur = kNone; return; }
-      --L.sp;
-      const uint2 e = stk[L.sp];
-      if (ANY || __uint_as_float(e.y) <= L.t) { L.cur = e.x; break; }
+      if (sp == 0) { finish(); return; }
+      --sp;
+      const uint2 e = stk[sp];
+      if (ANY || __uint_as_float(e.y) <= t) { cur = e.x; break; }
     }
-    if ((L.cur & kTlasBit) && L.in_obj) {  // back from a BLAS: restore the world-space ray
-      L.o = L.wo; L.d = L.wd; L.inv = rcp3(L.wd);
-      L.nodes = sc.nodes;
-      L.in_obj = false;
-      L.fast = L.wfast;
+    if ((cur & kTlasBit) && in_obj) {  // back from a BLAS: restore the world-space ray
+      o = wo; d = wd; inv = rcp3(wd);
+      signs = dir_signs(wd);
+      in_obj = false;
     }
-  };
-  auto finish = [&](bool hit) {
-    io.store(L.index, hit, L.t, L.h_inst, L.h_prim, L.h_u, L.h_v);
-    L.active = false;
-    L.cur = kNone;
-    L.sp = 0;
   };
 
   for (;;) {
     // ---- refill idle lanes from the queue
-    const unsigned idle = __ballot_sync(kFull, !L.active);
+    const unsigned idle = __ballot_sync(kFull, !active);
     if (idle != 0u && !exhausted && (__popc(idle) >= kRefillMin || idle == kFull)) {
       const int cnt = __popc(idle);
       int base = 0;
@@ -145,137 +235,132 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
       base = __shfl_sync(kFull, base, 0);
       if (base + cnt >= n) exhausted = true;
       const int mine = base + __popc(idle & lt_mask);
-      if (!L.active && mine < n) {
-        L.index = mine;
-        io.load(mine, L.wo, L.wd, L.t);
-        L.o = L.wo; L.d = L.wd; L.inv = rcp3(L.wd);
-        L.wfast = scene_fast && slab_fast_ok(L.wo, L.inv);
-        L.fast = L.wfast;
-        L.nodes = sc.nodes; L.tris = nullptr;
-        L.in_obj = false; L.cur_inst = -1; L.sp = 0;
-        L.h_inst = -1; L.h_prim = -1; L.h_u = 0.f; L.h_v = 0.f;
-        L.active = true;
-        // BVHAggregate pops node 0 and tests its bounds first (BVH.fs:45-47)
-        const float3 bmin = f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), bmax = f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]);
-        const bool pass = L.fast ? slab_pass<true>(slab<true>(bmin, bmax, L.o, L.inv), L.t) : slab_pass<false>(slab<false>(bmin, bmax, L.o, L.inv), L.t);
-        if (pass) L.cur = sc.tlas.root | kTlasBit;
-        else finish(false);
+      if (!active && mine < n) {
+        index = mine;
+        io.load(mine, wo, wd, t);
+        o = wo; d = wd; inv = rcp3(wd);
+        signs = dir_signs(wd);
+        in_obj = false; cur_inst = -1; sp = 0;
+        h_inst = -1; h_prim = -1; h_u = 0.f; h_v = 0.f;
+        active = true;
+        if (!(scene_fast && slab_fast_ok(wo, inv))) {
+          io.defer(index);
+          active = false;
+          cur = kNone;
+        } else {
+          // BVHAggregate pops node 0 and tests its bounds first (BVH.fs:45-47)
+          const Slab s = slab<true>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv);
+          if (slab_pass<true>(s, t)) cur = sc.tlas.root | kTlasBit;
+          else finish();
+        }
       }
     }
-    if (!__any_sync(kFull, L.active)) {
+    if (!__any_sync(kFull, active)) {
       if (exhausted) break;
       continue;
     }
 
     // ---- phase N: node steps until every active lane holds a leaf (or is done)
     for (;;) {
-      const bool want = L.active && !(L.cur & kLeafBit);
+      const bool want = active && !(cur & kLeafBit);
       if (!__any_sync(kFull, want)) break;
       if (want) {
-        const float4* np = reinterpret_cast<const float4*>(L.nodes + (L.cur & kIndexMask));
+        const float4* np = node_base + (size_t)(cur & kIndexMask) * 4u;
         const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-        Slab sl, sr;
-        bool pl, pr;
-        if (L.fast) {
-          sl = slab<true>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.o, L.inv);
-          sr = slab<true>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.o, L.inv);
-          pl = slab_pass<true>(sl, L.t); pr = slab_pass<true>(sr, L.t);
-        } else {
-          sl = slab<false>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.o, L.inv);
-          sr = slab<false>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.o, L.inv);
-          pl = slab_pass<false>(sl, L.t); pr = slab_pass<false>(sr, L.t);
-        }
-        const uint32_t level = L.cur & kTlasBit;
+        const Slab sl = slab<true>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
+        const Slab sr = slab<true>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
+        const bool pl = slab_pass<true>(sl, t), pr = slab_pass<true>(sr, t);
+        const uint32_t level = cur & kTlasBit;
+        const bool lf = ((signs >> fbits(n3.z)) & 1u) != 0u;  // left first iff dir[splitAxis] > 0 (BVH.fs:51-56 / Mesh.fs:235-240)
         const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
-        const uint32_t axis = fbits(n3.z);
-        const float dax = axis == 0 ? L.d.x : (axis == 1 ? L.d.y : (axis == 2 ? L.d.z : 1.f));
-        const bool left_first = dax > 0.f;  // BVH.fs:51-56 / Mesh.fs:235-240
-        const uint32_t nref = left_first ? left : right, fref = left_first ? right : left;
-        const bool pn = left_first ? pl : pr, pf = left_first ? pr : pl;
-        if (pn) {
-          L.cur = nref;
-          if (pf) { stk[L.sp] = make_uint2(fref, __float_as_uint(left_first ? sr.tmin : sl.tmin)); ++L.sp; }
-        } else if (pf) {
-          L.cur = fref;
+        if (pl & pr) {
+          cur = lf ? left : right;
+          stk[sp] = make_uint2(lf ? right : left, __float_as_uint(lf ? sr.tmin : sl.tmin));
+          ++sp;
+        } else if (pl | pr) {
+          cur = pl ? left : right;
         } else {
           pop();
         }
-        if (L.cur == kNone) finish(L.h_inst >= 0);
       }
     }
 
     // ---- phase E: PrimitiveInstance.Intersect (Primitive.fs:111-129); the world AABB
     // test already happened in the parent node
-    if (L.active && (L.cur & (kLeafBit | kTlasBit)) == (kLeafBit | kTlasBit)) {
-      const uint32_t slot = L.cur & kIndexMask;
+    if (active && (cur & (kLeafBit | kTlasBit)) == (kLeafBit | kTlasBit)) {
+      const uint32_t slot = cur & kIndexMask;
       const float4* ip = reinterpret_cast<const float4*>(sc.inst_trav + slot);
       const Mat43 M = load_mat43(ip);
       const float4 m0 = __ldg(ip + 3), m1 = __ldg(ip + 4), m2 = __ldg(ip + 5);
-      const float3 oo = transform_point(L.wo, M);  // Ray.Transform (Ray.fs:19-22)
-      const float3 od = transform_dir(L.wd, M);
-      bool descended = false;
+      const float3 oo = transform_point(wo, M);  // Ray.Transform (Ray.fs:19-22)
+      const float3 od = transform_dir(wd, M);
       if (fbits(m2.y)) {
         float tp;
-        const int root = sphere_test(m2.z, oo, od, L.t, tp);
+        const int root = sphere_test(m2.z, oo, od, t, tp);
         if (root) {
-          L.h_inst = (int)slot; L.h_prim = root - 1; L.h_u = 0.f; L.h_v = 0.f;
-          if (ANY) { finish(true); descended = true; }  // lane is done: nothing to pop
-          else L.t = tp;
+          h_inst = (int)slot; h_prim = root - 1; h_u = 0.f; h_v = 0.f;
+          if (ANY) finish();
+          else t = tp;
         }
+        if (active) pop();
       } else {
-        L.o = oo; L.d = od; L.inv = rcp3(od);
-        L.in_obj = true;
-        L.fast = scene_fast && slab_fast_ok(oo, L.inv);
-        L.cur_inst = (int)slot;
-        L.nodes = sc.nodes + fbits(m1.w);
-        L.tris = sc.tris + fbits(m2.x);
-        // MeshPrimitive pops BLAS node 0 and tests its bounds first (Mesh.fs:224-227)
-        const float3 bmin = f3(m0.x, m0.y, m0.z), bmax = f3(m1.x, m1.y, m1.z);
-        const bool pass = L.fast ? slab_pass<true>(slab<true>(bmin, bmax, L.o, L.inv), L.t) : slab_pass<false>(slab<false>(bmin, bmax, L.o, L.inv), L.t);
-        if (pass) { L.cur = fbits(m0.w); descended = true; }
-      }
-      if (!descended) {
-        pop();
-        if (L.cur == kNone) finish(L.h_inst >= 0);
+        o = oo; d = od; inv = rcp3(od);
+        signs = dir_signs(od);
+        in_obj = true;
+        cur_inst = (int)slot;
+        if (!slab_fast_ok(oo, inv)) {
+          io.defer(index);  // re-traced from scratch by the fix-up kernel
+          active = false;
+          cur = kNone;
+        } else {
+          // MeshPrimitive pops BLAS node 0 and tests its bounds first (Mesh.fs:224-227)
+          const Slab s = slab<true>(f3(m0.x, m0.y, m0.z), f3(m1.x, m1.y, m1.z), o, inv);
+          if (slab_pass<true>(s, t)) cur = fbits(m0.w);
+          else pop();
+        }
       }
     }
 
     // ---- phase T: triangles of the held BLAS leaf in slot order, each behind its own
-    // exact AABB test (Mesh.fs:229-233 — load-bearing)
+    // AABB test (Mesh.fs:229-233 — load-bearing)
     {
-      bool has = L.active && (L.cur & (kLeafBit | kTlasBit)) == kLeafBit;
-      const uint32_t count = has ? ((L.cur >> 24) & 63u) : 0u;
-      const uint32_t first = L.cur & kFirstMask;
+      bool has = active && (cur & (kLeafBit | kTlasBit)) == kLeafBit;
+      const uint32_t count = has ? ((cur >> 27) & 7u) : 0u;
+      const uint32_t first = cur & kFirstMask;
       for (uint32_t k = 0;; ++k) {
         const bool more = has && k < count;
         if (!__any_sync(kFull, more)) break;
         if (more) {
-          const float4* tp4 = reinterpret_cast<const float4*>(L.tris + first + k);
+          const float4* tp4 = tri_base + (size_t)(first + k) * 3u;
           const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
           const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
-          bool box;
-          if (L.fast) {  // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
-            const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-            const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-            box = slab_pass<true>(slab<true>(lo, hi, L.o, L.inv), L.t);
-          } else {
-            const float3 lo = min_native(min_native(p0, p1), p2);
-            const float3 hi = max_native(max_native(p0, p1), p2);
-            box = slab_pass<false>(slab<false>(lo, hi, L.o, L.inv), L.t);
-          }
+          // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
+          const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+          const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
           float tp, u, v;
-          if (box && tri_test(p0, p1, p2, L.o, L.d, L.t, tp, u, v)) {
-            L.h_inst = L.cur_inst; L.h_prim = (int)(first + k); L.h_u = u; L.h_v = v;
-            if (ANY) { finish(true); has = false; }
-            else L.t = tp;
+          if (slab_pass<true>(slab<true>(lo, hi, o, inv), t) && tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
+            h_inst = cur_inst; h_prim = (int)(first + k); h_u = u; h_v = v;
+            if (ANY) { finish(); has = false; }
+            else t = tp;
           }
         }
       }
-      if (has) {
-        pop();
-        if (L.cur == kNone) finish(L.h_inst >= 0);
-      }
+      if (has) pop();
     }
+  }
+}
+
+// Fix-up: the deferred rays, one per thread, exact path.
+template <bool ANY, class IO>
+BN_DEV void traverse_deferred(const DScene& sc, IO& io, const int* __restrict__ list, int n_deferred) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_deferred; k += gridDim.x * blockDim.x) {
+    const int i = list[k];
+    float3 o, d;
+    float t;
+    io.load(i, o, d, t);
+    TraceResult r;
+    trace_exact<ANY>(sc, o, d, t, r);
+    io.store(i, r);
   }
 }
 

@@ -2,5 +2,5 @@
 #pragma once
 namespace bn {
 constexpr int kStackSize = 96;     // unified TLAS+BLAS traversal stack entries per ray
-constexpr int kMaxLeafCount = 63;  // 6-bit item count in a leaf reference
+constexpr int kMaxLeafCount = 7;   // 3-bit triangle count in a BLAS leaf reference (the reference builds leaves of <= 4)
 }  // namespace bn

@@ -161,7 +161,11 @@ enum {
   BN_RENDER_TRACE_NULL_SHADOW = 1u << 0,
   /* bracket every kernel launch with CUDA events on the launching stream and
    * report per-class device time in BnStats.{extend,shade,shadow,other}_ms */
-  BN_RENDER_PROFILE = 1u << 1
+  BN_RENDER_PROFILE = 1u << 1,
+  /* route EVERY ray through the exact (reference-op-for-op) traversal of the
+   * fix-up kernel instead of the fast phases: slow; exists so tests can show the
+   * two paths agree bit for bit on real path-tracing rays */
+  BN_RENDER_FORCE_EXACT = 1u << 2
 };
 
 typedef struct BnStats {

@@ -65,6 +65,19 @@ def test_film_bitwise_and_ray_counts(name, w, h, spp):
     assert bits_equal(gf2, of).all() and gst2.shadow_rays == ost["shadow_rays"]
 
 
+def test_exact_fixup_path_agrees_on_render_rays():
+    """BN_RENDER_FORCE_EXACT sends every extend / shadow ray through the fix-up kernel's
+    op-for-op traversal; the film must not change by a bit."""
+    set_portable_math(True)
+    for name in ("cbox_bunny", "material_sweep"):
+        scene = load_scene(name)
+        p = make_params(48, 48, 3)
+        fast, st = scene.gpu().render(p)
+        exact, st2 = scene.gpu().render(make_params(48, 48, 3, flags=_ffi.BN_RENDER_FORCE_EXACT))
+        assert bits_equal(fast, exact).all()
+        assert (st.extend_rays, st.shadow_rays) == (st2.extend_rays, st2.shadow_rays)
+
+
 def test_window_and_sample_range_sharding():
     """Multi-GPU sharding contract: a tile window / sample range renders exactly the
     same paths as the full render (seeds depend only on x, y, sampleId)."""
