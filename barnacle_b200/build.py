@@ -64,6 +64,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static"]
     _run(cmd, verbose)
+    # C++ CLI mirroring Program.fs (links the C ABI only)
+    cli = os.path.join(LIB_DIR, "barnacle_gpu")
+    _run([HOST_CXX, "-std=c++17", "-O2", os.path.join(CSRC, "cli", "barnacle_gpu.cpp"), "-o", cli, "-L" + LIB_DIR, "-lbarnacle_b200",
+          "-Wl,-rpath,$ORIGIN"], verbose)
     return LIB
 
 
