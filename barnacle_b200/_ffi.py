@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbarnacle_b200.so")
+LIB_PATH = os.environ.get("BN_LIB") or os.path.join(_HERE, "lib", "libbarnacle_b200.so")  # BN_LIB: experiment builds only
 
 BN_OK = 0
 BN_ERR_INVALID, BN_ERR_CUDA, BN_ERR_NO_DEVICE, BN_ERR_IO, BN_ERR_NO_LIGHT = -1, -2, -3, -4, -5

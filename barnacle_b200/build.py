@@ -47,8 +47,22 @@ def _all_inputs() -> list[str]:
     return out
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and _newer(LIB, _all_inputs()):
+def build(force: bool = False, verbose: bool = False, stats: bool = False, defines: list[str] | None = None, out: str | None = None) -> str:
+    """stats=True: debug build with traversal phase counters (-DBN_TRAV_STATS); never shipped.
+    defines/out: experiment variants (tools/), written next to the real library."""
+    global LIB
+    defines = defines or []
+    lib_real = LIB
+    if out:
+        LIB = os.path.join(LIB_DIR, out)
+    try:
+        return _build(force or bool(out) or bool(defines), verbose, stats, defines)
+    finally:
+        LIB = lib_real
+
+
+def _build(force: bool, verbose: bool, stats: bool, defines: list[str]) -> str:
+    if not force and not stats and _newer(LIB, _all_inputs()):
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     objs = []
@@ -59,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     for src in CUDA_SOURCES:
         obj = os.path.join(OBJ_DIR, src.replace("/", "_") + ".o")
-        cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *NVCC_FLAGS, *(["-DBN_TRAV_STATS"] if stats else []), *["-D" + d for d in defines], *(["-Xptxas", "-v"] if verbose else []), "-c", os.path.join(CSRC, src), "-o", obj]
         _run(cmd, verbose)
         objs.append(obj)
     cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static"]
@@ -82,4 +96,6 @@ def _run(cmd: list[str], verbose: bool) -> None:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv or "--verbose" in sys.argv))
+    _defs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--define=")]
+    _out = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv or "--verbose" in sys.argv, stats="--stats" in sys.argv, defines=_defs, out=_out))

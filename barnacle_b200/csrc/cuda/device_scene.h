@@ -75,6 +75,15 @@ struct __align__(16) GInstHead {  // shading-side instance record (48 B)
 };
 static_assert(sizeof(GInstHead) == 48, "GInstHead must be 48 B");
 
+// Small-TLAS fast path: for each of the 8 direction octants, the instances in the
+// order the reference's TLAS walk reaches them (the order depends only on the signs
+// of the ray direction), each with its world AABB: 32 B per entry.
+struct __align__(16) GFlatInst {
+  float bmin[3]; uint32_t slot;
+  float bmax[3]; uint32_t pad;
+};
+constexpr uint32_t kFlatTlasMax = 16;  // use the ordered scan when the scene has at most this many instances
+
 struct __align__(16) GMat43 { float m[12]; };  // rows 1..4 x columns 1..3 of a Matrix4x4
 
 struct __align__(16) GMaterial { uint32_t type; float r, g, b; float p0, p1, pad0, pad1; };
@@ -104,6 +113,7 @@ struct DScene {
   const uint32_t* light_inst;
   uint32_t n_inst, n_light_inst;
   uint32_t all_finite;       // every box / vertex / matrix is finite: the fast slab path is exact (vecmath.cuh)
+  const GFlatInst* flat_tlas;  // [8][n_inst] or nullptr when n_inst > kFlatTlasMax
   GCamera cam;
 };
 

@@ -37,6 +37,12 @@ void set_error(const std::string& msg);
 namespace bn {
 
 constexpr int kBlock = 128;
+#ifndef BN_TRAV_MIN_BLOCKS
+#define BN_TRAV_MIN_BLOCKS 8   // resident CTAs per SM the traversal kernels are compiled for (register cap)
+#endif
+#ifndef BN_TRAV_GRID_MULT
+#define BN_TRAV_GRID_MULT 8    // persistent grid = SMs x this
+#endif
 
 struct WaveParams {
   int width, height;
@@ -137,7 +143,7 @@ struct ExtendIO {
   BN_DEV void defer(int i) const { deferred.push(i); }
 };
 template <bool ANY, class IO>
-__global__ void __launch_bounds__(kBlock, 8) k_traverse(DScene sc, IO io) {
+__global__ void __launch_bounds__(kBlock, BN_TRAV_MIN_BLOCKS) k_traverse(DScene sc, IO io) {
   traverse_persistent<ANY>(sc, io);
 }
 template <bool ANY, class IO>
@@ -503,6 +509,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     BN_CUDA(cudaMemsetAsync(s->counters, 0, need * sizeof(int), stream));
     BN_CUDA(cudaMemsetAsync(s->shadow_ref, 0, sizeof(unsigned long long), stream));
     const int grid = s->num_sms * 8;
+    const int tgrid = s->num_sms * BN_TRAV_GRID_MULT;
     DScene dsc = s->d;
     if (p->flags & BN_RENDER_FORCE_EXACT) dsc.all_finite = 0u;  // every ray is deferred to the exact fix-up kernel
     // BN_RENDER_PROFILE: bracket every launch with events on the launching stream
@@ -554,7 +561,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         for (int b = 0; b < D; ++b) {
           prof_begin(0);
           const ExtendIO eio{A, A + cp, s->hits, n_active + b, cursors + 3 * b, DeferList{n_defer + 2 * b, s->defer_list}};
-          k_traverse<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
+          k_traverse<false, ExtendIO><<<tgrid, kBlock, 0, stream>>>(dsc, eio);
           k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
           prof_end();
           prof_begin(1);
@@ -564,7 +571,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
           prof_end();
           prof_begin(2);
           const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b, cursors + 3 * b + 2, DeferList{n_defer + 2 * b + 1, s->defer_list}};
-          k_traverse<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
+          k_traverse<true, ShadowIO><<<tgrid, kBlock, 0, stream>>>(dsc, sio);
           k_traverse_fixup<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
           prof_end();
           launches += 5;
@@ -621,6 +628,15 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
 
 extern "C" {
 
+#ifdef BN_TRAV_STATS
+// debug builds only: [closest: cntN cntT cntE cntAll sumN sumT sumE sumAll | any: same]
+__attribute__((visibility("default"))) int bn_debug_trav_stats(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, bn::g_trav_stats, sizeof(unsigned long long) * 20);
+  if (reset) { unsigned long long z[20] = {0}; cudaMemcpyToSymbol(bn::g_trav_stats, z, sizeof z); }
+  return 0;
+}
+#endif
+
 int bn_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -656,6 +672,10 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   d.n_inst = (uint32_t)cs.inst_head.size();
   d.n_light_inst = (uint32_t)cs.light_inst.size();
   d.all_finite = cs.all_finite ? 1u : 0u;
+  d.flat_tlas = nullptr;
+  if (!cs.flat_tlas.empty() && !std::getenv("BN_NO_FLAT_TLAS")) {
+    if ((rc = upload(s, cs.flat_tlas, &d.flat_tlas))) { bn_scene_destroy(s); return rc; }
+  }
   d.cam = cs.cam;
   if (cudaMalloc((void**)&s->shadow_ref, sizeof(unsigned long long)) != cudaSuccess) { bn_scene_destroy(s); bnhost::set_error("cudaMalloc failed"); return BN_ERR_CUDA; }
   *out = s;

@@ -238,6 +238,38 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       return false;
     }
   }
+  // Small-TLAS ordered scan (traverse.cuh): instance order of the reference's walk for each octant.
+  // The walk visits left first iff dir[splitAxis] > 0 (Aggregate/BVH.fs:51-56) and leaf items in
+  // slot order (:49-50), so the order is a function of the three sign bits only.
+  if (d.instance_count <= bn::kFlatTlasMax) {
+    out.flat_tlas.resize((size_t)8 * d.instance_count);
+    for (uint32_t oct = 0; oct < 8; ++oct) {
+      std::vector<uint32_t> order;
+      std::vector<uint32_t> stack{0u};
+      while (!stack.empty()) {
+        const uint32_t i = stack.back();
+        stack.pop_back();
+        const BnBVHNode& nd = d.tlas_nodes[i];
+        if (nd.is_leaf) {
+          for (int k = 0; k < nd.count; ++k) order.push_back((uint32_t)(nd.right_or_offset + k));
+        } else if ((oct >> nd.split_axis) & 1u) {  // dir[axis] > 0: push right, then left (popped first)
+          stack.push_back((uint32_t)nd.right_or_offset);
+          stack.push_back(i + 1);
+        } else {
+          stack.push_back(i + 1);
+          stack.push_back((uint32_t)nd.right_or_offset);
+        }
+      }
+      if (order.size() != d.instance_count) { err = "TLAS does not cover every instance exactly once"; return false; }
+      for (uint32_t k = 0; k < d.instance_count; ++k) {
+        bn::GFlatInst& f = out.flat_tlas[(size_t)oct * d.instance_count + k];
+        const BnInstance& in = d.instances[order[k]];
+        std::memcpy(f.bmin, in.bounds_min, 12); std::memcpy(f.bmax, in.bounds_max, 12);
+        f.slot = order[k];
+        f.pad = 0;
+      }
+    }
+  }
   out.light_inst.assign(d.light_instances, d.light_instances + d.light_instance_count);
   for (uint32_t li : out.light_inst)
     if (li >= d.instance_count || d.instances[li].light_id < 0) { err = "light instance list is inconsistent"; return false; }

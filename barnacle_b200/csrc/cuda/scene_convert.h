@@ -21,6 +21,7 @@ struct ConvertedScene {
   std::vector<bn::GMaterial> materials;
   std::vector<bn::GLight> lights;
   std::vector<uint32_t> light_inst;
+  std::vector<bn::GFlatInst> flat_tlas;  // 8 * n_inst entries, empty when the TLAS is not small
   bn::GCamera cam;
   int max_stack = 0;
   bool all_finite = true;

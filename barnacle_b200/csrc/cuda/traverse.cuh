@@ -14,12 +14,13 @@
 // child is re-checked with its stored entry distance instead of re-fetching
 // its box; `tmin <= Min(t, thi)` == `(tmin <= t) && (tmin <= thi)`.
 //
-// Execution model: a persistent, warp-synchronous loop.  Every lane owns one ray;
-// the warp alternates between three phases so that lanes doing the same kind of
-// work do it together (SIMT efficiency is what bounds this kernel, not DRAM):
-//   N  node steps (64-B GNode, two slab tests) until every lane holds a leaf
+// Execution model: a persistent, warp-synchronous loop.  Every lane owns one ray
+// and is in one of three states; each iteration the warp votes and runs the ONE
+// phase most lanes are ready for, so that lanes doing the same kind of work do it
+// together (SIMT efficiency is what bounds this kernel, not DRAM):
+//   N  one node step (64-B GNode, two slab tests)
 //   E  enter instance: ray -> object space, BLAS root / sphere test
-//   T  triangles of the held BLAS leaf, one triangle per step across the lanes
+//   T  the next triangle of the held BLAS leaf
 // Lanes whose ray is finished are refilled from the global queue (one
 // warp-aggregated atomic) as soon as enough of them are idle.
 //
@@ -39,9 +40,21 @@ namespace bn {
 constexpr uint32_t kTlasBit = 0x40000000u;
 constexpr uint32_t kIndexMask = 0x3FFFFFFFu;
 constexpr uint32_t kFirstMask = 0x07FFFFFFu;
-constexpr uint32_t kNone = 0xFFFFFFFFu;  // "stack empty": a leaf ref that no scene can produce
+constexpr uint32_t kNone = 0xFFFFFFFFu;  // lane idle (a leaf ref that no scene can produce)
+constexpr uint32_t kScan = 0xFFFFFFFEu;  // lane is at the small-TLAS ordered scan (ditto)
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kRefillMin = 8;            // refill when at least this many lanes are idle
+#ifndef BN_REFILL_MIN
+#define BN_REFILL_MIN 8
+#endif
+constexpr int kRefillMin = BN_REFILL_MIN;  // refill when at least this many lanes are idle
+
+#ifdef BN_TRAV_STATS
+// debug builds only (python -m barnacle_b200.build --stats): phase executions and ready lanes
+__device__ unsigned long long g_trav_stats[20];
+#define BN_STAT(slot, lanes) do { if ((threadIdx.x & 31) == 0) { st_cnt[slot] += 1; st_sum[slot] += (lanes); } } while (0)
+#else
+#define BN_STAT(slot, lanes) do { } while (0)
+#endif
 
 BN_DEV uint32_t fbits(float f) { return __float_as_uint(f); }
 
@@ -182,24 +195,32 @@ template <bool ANY, class IO>
 BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
   uint2 stk[kStackSize];  // (ref, entry distance bits)
   // per-lane state
-  float3 wo, wd;          // world-space ray
+  float3 wo, wd, winv;    // world-space ray
   float3 o, d, inv;       // ray in the CURRENT space
   float t = 0.f;          // closest distance so far (ANY: the fixed tmax)
   int h_inst = -1, h_prim = -1;
   float h_u = 0.f, h_v = 0.f;
-  uint32_t cur = kNone;   // ref being processed
+  uint32_t cur = kNone;   // ref being processed; kScan: next instance of the flat TLAS; kNone: lane idle
   uint32_t signs = 8u;    // dir_signs of the current-space direction
+  uint32_t wsigns = 8u;   // ... of the world-space direction
   int sp = 0;
   int cur_inst = -1;
   int index = 0;          // queue slot of this ray
-  bool in_obj = false, active = false;
-  wo = wd = o = d = inv = splat(0.f);
+  uint32_t tri_k = 0;     // next triangle of the held BLAS leaf
+  uint32_t tl_pos = 0;    // next entry of the flat TLAS order
+  bool in_obj = false;
+  wo = wd = winv = o = d = inv = splat(0.f);
 
+#ifdef BN_TRAV_STATS
+  unsigned long long st_cnt[5] = {0, 0, 0, 0, 0}, st_sum[5] = {0, 0, 0, 0, 0};
+#endif
   const int n = io.count();
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   bool exhausted = false;
   const bool scene_fast = sc.all_finite != 0u;
+  const bool flat = sc.flat_tlas != nullptr;
+  const uint32_t n_inst = sc.n_inst;
   const float4* const node_base = reinterpret_cast<const float4*>(sc.nodes);
   const float4* const tri_base = reinterpret_cast<const float4*>(sc.tris);
 
@@ -207,46 +228,57 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
     TraceResult r;
     r.hit = h_inst >= 0; r.t = t; r.inst = h_inst; r.prim = h_prim; r.u = h_u; r.v = h_v;
     io.store(index, r);
-    active = false;
     cur = kNone;
   };
-  // pops the next entry whose stored entry distance still passes; finishes the ray if none
+  // pops the next entry whose stored entry distance still passes
   auto pop = [&]() {
     for (;;) {
-      if (sp == 0) { finish(); return; }
+      if (sp == 0) {
+        if (flat) cur = kScan;  // BLAS exhausted: back to the ordered instance scan (world ray is kept in wo/winv)
+        else finish();
+        return;
+      }
       --sp;
       const uint2 e = stk[sp];
       if (ANY || __uint_as_float(e.y) <= t) { cur = e.x; break; }
     }
-    if ((cur & kTlasBit) && in_obj) {  // back from a BLAS: restore the world-space ray
-      o = wo; d = wd; inv = rcp3(wd);
-      signs = dir_signs(wd);
+    if ((cur & kTlasBit) && in_obj) {  // tree TLAS: back from a BLAS, restore the world-space ray
+      o = wo; d = wd; inv = winv;
+      signs = wsigns;
       in_obj = false;
     }
   };
 
   for (;;) {
+    // ---- one vote: how many lanes are ready for each phase (a single REDUX)
+    const bool isN = !(cur & kLeafBit);
+    const bool isT = (cur >> 30) == 2u;
+    const bool isS = cur == kScan;
+    const bool isE = (cur >> 30) == 3u && cur < kScan;
+    const uint32_t votes = __reduce_add_sync(kFull, isN ? 1u : (isT ? (1u << 8) : (isE ? (1u << 16) : (isS ? (1u << 24) : 0u))));
+    const int nN = (int)(votes & 255u), nT = (int)((votes >> 8) & 255u), nE = (int)((votes >> 16) & 255u), nS = (int)(votes >> 24);
+    const int n_idle = 32 - (nN + nT + nE + nS);
+
     // ---- refill idle lanes from the queue
-    const unsigned idle = __ballot_sync(kFull, !active);
-    if (idle != 0u && !exhausted && (__popc(idle) >= kRefillMin || idle == kFull)) {
-      const int cnt = __popc(idle);
+    if (n_idle != 0 && !exhausted && (n_idle >= kRefillMin || n_idle == 32)) {
+      const unsigned idle = __ballot_sync(kFull, cur == kNone);
       int base = 0;
-      if (lane == 0) base = atomicAdd(io.cursor(), cnt);
+      if (lane == 0) base = atomicAdd(io.cursor(), n_idle);
       base = __shfl_sync(kFull, base, 0);
-      if (base + cnt >= n) exhausted = true;
+      if (base + n_idle >= n) exhausted = true;
       const int mine = base + __popc(idle & lt_mask);
-      if (!active && mine < n) {
+      if (cur == kNone && mine < n) {
         index = mine;
         io.load(mine, wo, wd, t);
-        o = wo; d = wd; inv = rcp3(wd);
-        signs = dir_signs(wd);
-        in_obj = false; cur_inst = -1; sp = 0;
+        winv = rcp3(wd);
+        wsigns = dir_signs(wd);
+        o = wo; d = wd; inv = winv; signs = wsigns;
+        in_obj = false; cur_inst = -1; sp = 0; tri_k = 0; tl_pos = 0;
         h_inst = -1; h_prim = -1; h_u = 0.f; h_v = 0.f;
-        active = true;
-        if (!(scene_fast && slab_fast_ok(wo, inv))) {
+        if (!(scene_fast && slab_fast_ok(wo, winv))) {
           io.defer(index);
-          active = false;
-          cur = kNone;
+        } else if (flat) {
+          cur = kScan;
         } else {
           // BVHAggregate pops node 0 and tests its bounds first (BVH.fs:45-47)
           const Slab s = slab<true>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv);
@@ -254,17 +286,15 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
           else finish();
         }
       }
+      continue;  // re-vote with the new rays
     }
-    if (!__any_sync(kFull, active)) {
-      if (exhausted) break;
-      continue;
-    }
+    if (n_idle == 32) break;  // nothing in flight and the queue is exhausted
+    BN_STAT(3, 32 - n_idle);
 
-    // ---- phase N: node steps until every active lane holds a leaf (or is done)
-    for (;;) {
-      const bool want = active && !(cur & kLeafBit);
-      if (!__any_sync(kFull, want)) break;
-      if (want) {
+    if (nN >= nT && nN >= nE && nN >= nS) {
+      // ---- phase N: one node step (64-B GNode, two slab tests)
+      BN_STAT(0, nN);
+      if (isN) {
         const float4* np = node_base + (size_t)(cur & kIndexMask) * 4u;
         const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
         const Slab sl = slab<true>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
@@ -283,71 +313,96 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
           pop();
         }
       }
-    }
-
-    // ---- phase E: PrimitiveInstance.Intersect (Primitive.fs:111-129); the world AABB
-    // test already happened in the parent node
-    if (active && (cur & (kLeafBit | kTlasBit)) == (kLeafBit | kTlasBit)) {
-      const uint32_t slot = cur & kIndexMask;
-      const float4* ip = reinterpret_cast<const float4*>(sc.inst_trav + slot);
-      const Mat43 M = load_mat43(ip);
-      const float4 m0 = __ldg(ip + 3), m1 = __ldg(ip + 4), m2 = __ldg(ip + 5);
-      const float3 oo = transform_point(wo, M);  // Ray.Transform (Ray.fs:19-22)
-      const float3 od = transform_dir(wd, M);
-      if (fbits(m2.y)) {
-        float tp;
-        const int root = sphere_test(m2.z, oo, od, t, tp);
-        if (root) {
-          h_inst = (int)slot; h_prim = root - 1; h_u = 0.f; h_v = 0.f;
-          if (ANY) finish();
+    } else if (nT >= nE && nT >= nS) {
+      // ---- phase T: next triangle of the held BLAS leaf (slot order), behind its own
+      // AABB test (Mesh.fs:229-233 — load-bearing)
+      BN_STAT(1, nT);
+      if (isT) {
+        const uint32_t count = (cur >> 27) & 7u;
+        const uint32_t tri = (cur & kFirstMask) + tri_k;
+        const float4* tp4 = tri_base + (size_t)tri * 3u;
+        const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
+        const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
+        // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
+        const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+        const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+        float tp, u, v;
+        bool done = false;
+        if (slab_pass<true>(slab<true>(lo, hi, o, inv), t) && tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
+          h_inst = cur_inst; h_prim = (int)tri; h_u = u; h_v = v;
+          if (ANY) { finish(); done = true; }
           else t = tp;
         }
-        if (active) pop();
-      } else {
-        o = oo; d = od; inv = rcp3(od);
-        signs = dir_signs(od);
-        in_obj = true;
-        cur_inst = (int)slot;
-        if (!slab_fast_ok(oo, inv)) {
-          io.defer(index);  // re-traced from scratch by the fix-up kernel
-          active = false;
-          cur = kNone;
-        } else {
-          // MeshPrimitive pops BLAS node 0 and tests its bounds first (Mesh.fs:224-227)
-          const Slab s = slab<true>(f3(m0.x, m0.y, m0.z), f3(m1.x, m1.y, m1.z), o, inv);
-          if (slab_pass<true>(s, t)) cur = fbits(m0.w);
-          else pop();
+        if (!done) {
+          ++tri_k;
+          if (tri_k >= count) { tri_k = 0; pop(); }
         }
       }
-    }
-
-    // ---- phase T: triangles of the held BLAS leaf in slot order, each behind its own
-    // AABB test (Mesh.fs:229-233 — load-bearing)
-    {
-      bool has = active && (cur & (kLeafBit | kTlasBit)) == kLeafBit;
-      const uint32_t count = has ? ((cur >> 27) & 7u) : 0u;
-      const uint32_t first = cur & kFirstMask;
-      for (uint32_t k = 0;; ++k) {
-        const bool more = has && k < count;
-        if (!__any_sync(kFull, more)) break;
-        if (more) {
-          const float4* tp4 = tri_base + (size_t)(first + k) * 3u;
-          const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
-          const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
-          // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
-          const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-          const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-          float tp, u, v;
-          if (slab_pass<true>(slab<true>(lo, hi, o, inv), t) && tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
-            h_inst = cur_inst; h_prim = (int)(first + k); h_u = u; h_v = v;
-            if (ANY) { finish(); has = false; }
+    } else if (nE >= nS) {
+      // ---- phase E: PrimitiveInstance.Intersect (Primitive.fs:111-129); the world AABB
+      // test already happened (parent node / ordered scan)
+      BN_STAT(2, nE);
+      if (isE) {
+        const uint32_t slot = cur & kIndexMask;
+        const float4* ip = reinterpret_cast<const float4*>(sc.inst_trav + slot);
+        const Mat43 M = load_mat43(ip);
+        const float4 m0 = __ldg(ip + 3), m1 = __ldg(ip + 4), m2 = __ldg(ip + 5);
+        const float3 oo = transform_point(wo, M);  // Ray.Transform (Ray.fs:19-22)
+        const float3 od = transform_dir(wd, M);
+        tri_k = 0;
+        if (fbits(m2.y)) {
+          float tp;
+          const int root = sphere_test(m2.z, oo, od, t, tp);
+          bool done = false;
+          if (root) {
+            h_inst = (int)slot; h_prim = root - 1; h_u = 0.f; h_v = 0.f;
+            if (ANY) { finish(); done = true; }
             else t = tp;
+          }
+          if (!done) pop();
+        } else {
+          o = oo; d = od; inv = rcp3(od);
+          signs = dir_signs(od);
+          in_obj = true;
+          cur_inst = (int)slot;
+          if (!slab_fast_ok(oo, inv)) {
+            io.defer(index);  // re-traced from scratch by the fix-up kernel
+            cur = kNone;
+          } else {
+            // MeshPrimitive pops BLAS node 0 and tests its bounds first (Mesh.fs:224-227)
+            const Slab s = slab<true>(f3(m0.x, m0.y, m0.z), f3(m1.x, m1.y, m1.z), o, inv);
+            if (slab_pass<true>(s, t)) cur = fbits(m0.w);
+            else pop();
           }
         }
       }
-      if (has) pop();
+    } else {
+      // ---- phase S (small TLAS): scan the octant-ordered instance list for the next world
+      // AABB the ray passes with the CURRENT t.  In the fast path a passing instance box
+      // implies passing boxes for all its TLAS ancestors (they contain it, were tested
+      // earlier against a larger t, and no lane can be NaN), so skipping the interior TLAS
+      // nodes changes neither the set nor the order of instances entered.
+      BN_STAT(4, nS);
+      if (isS) {
+        const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns & 7u) * n_inst);
+        bool found = false;
+        while (tl_pos < n_inst) {
+          const float4 a = __ldg(fp + 2u * tl_pos), b = __ldg(fp + 2u * tl_pos + 1u);
+          ++tl_pos;
+          if (slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) {
+            cur = kLeafBit | kTlasBit | fbits(a.w);
+            found = true;
+            break;
+          }
+        }
+        if (!found) finish();
+      }
     }
   }
+#ifdef BN_TRAV_STATS
+  if (lane == 0)
+    for (int k = 0; k < 5; ++k) { atomicAdd(&g_trav_stats[(ANY ? 10 : 0) + k], st_cnt[k]); atomicAdd(&g_trav_stats[(ANY ? 10 : 0) + 5 + k], st_sum[k]); }
+#endif
 }
 
 // Fix-up: the deferred rays, one per thread, exact path.
