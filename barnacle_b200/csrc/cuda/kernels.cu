@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,9 @@ namespace bn {
 constexpr int kBlock = 128;
 #ifndef BN_TRAV_MIN_BLOCKS
 #define BN_TRAV_MIN_BLOCKS 8   // resident CTAs per SM the traversal kernels are compiled for (register cap)
+#endif
+#ifndef BN_SHADE_MIN_BLOCKS
+#define BN_SHADE_MIN_BLOCKS 6
 #endif
 #ifndef BN_TRAV_GRID_MULT
 #define BN_TRAV_GRID_MULT 8    // persistent grid = SMs x this
@@ -152,15 +156,17 @@ __global__ void __launch_bounds__(kBlock) k_traverse_fixup(DScene sc, IO io) {
 }
 
 // ---- shade: one iteration of Li's loop body (PathTracing.fs:30-79) --------------------
-__global__ void __launch_bounds__(kBlock) k_shade(DScene sc, WaveParams wp, int bounce, const float4* __restrict__ s0, const float4* __restrict__ s1,
+__global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc, WaveParams wp, int bounce, const float4* __restrict__ s0, const float4* __restrict__ s1,
                                                   const float4* __restrict__ s2, const float4* __restrict__ hits, float4* __restrict__ o0,
                                                   float4* __restrict__ o1, float4* __restrict__ o2, float4* __restrict__ q0, float4* __restrict__ q1,
                                                   float4* __restrict__ q2, float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr,
                                                   int* n_out, int* n_shadow, int* cursor, unsigned long long* shadow_ref) {
   const int n = *n_ptr;
+  int next = warp_fetch(cursor);
   for (;;) {
-    const int base = warp_fetch(cursor);
+    const int base = next;
     if (base >= n) break;
+    next = warp_fetch(cursor);  // claimed one chunk ahead: the atomic's round trip overlaps this chunk's shading
     const int i = base + lane_id();
     bool alive = false, has_shadow = false, ref_shadow = false;
     float3 P = splat(0.f), nd = splat(0.f), beta = splat(0.f);
@@ -413,6 +419,21 @@ struct BnScene {
 
 namespace {
 
+// Wave buffers are large (hundreds of MB) and identical from scene to scene; a managed host
+// that re-creates the scene every frame must not pay cudaMalloc/cudaFree for
+// them each time.  One parked set per device.
+struct WaveBuffers {
+  int device = -1;
+  size_t cap = 0;
+  float4* state[2] = {nullptr, nullptr};
+  float4* hits = nullptr;
+  float4* shq = nullptr;
+  float4* rad = nullptr;
+  int* defer_list = nullptr;
+};
+std::mutex g_pool_mutex;
+std::vector<WaveBuffers> g_pool;
+
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
   bnhost::set_error(std::string(what) + ": " + cudaGetErrorString(e));
@@ -441,11 +462,44 @@ size_t wave_capacity_paths() {
   return (v + 31) & ~(size_t)31;
 }
 
+void free_wave_buffers(WaveBuffers& w) {
+  for (void* p : {(void*)w.state[0], (void*)w.state[1], (void*)w.hits, (void*)w.shq, (void*)w.rad, (void*)w.defer_list})
+    if (p) cudaFree(p);
+  w = WaveBuffers();
+}
+
+void release_wave_buffers(BnScene* s) {  // park the scene's buffers for the next scene on this device
+  if (s->cap == 0) return;
+  WaveBuffers w;
+  w.device = s->device; w.cap = s->cap;
+  w.state[0] = s->state[0]; w.state[1] = s->state[1]; w.hits = s->hits; w.shq = s->shq; w.rad = s->rad; w.defer_list = s->defer_list;
+  s->cap = 0;
+  s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (WaveBuffers& p : g_pool)
+    if (p.device == w.device) {
+      if (p.cap >= w.cap) { free_wave_buffers(w); return; }
+      free_wave_buffers(p);
+      p = w;
+      return;
+    }
+  g_pool.push_back(w);
+}
+
 int ensure_wave_buffers(BnScene* s, size_t cap) {
   if (s->cap >= cap) return BN_OK;
-  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list})
-    if (p) cudaFree(p);
-  s->cap = 0;
+  release_wave_buffers(s);
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (size_t k = 0; k < g_pool.size(); ++k)
+      if (g_pool[k].device == s->device && g_pool[k].cap >= cap) {
+        const WaveBuffers w = g_pool[k];
+        g_pool.erase(g_pool.begin() + (long)k);
+        s->cap = w.cap;
+        s->state[0] = w.state[0]; s->state[1] = w.state[1]; s->hits = w.hits; s->shq = w.shq; s->rad = w.rad; s->defer_list = w.defer_list;
+        return BN_OK;
+      }
+  }
   BN_CUDA(cudaMalloc((void**)&s->state[0], cap * 3 * sizeof(float4)));
   BN_CUDA(cudaMalloc((void**)&s->state[1], cap * 3 * sizeof(float4)));
   BN_CUDA(cudaMalloc((void**)&s->hits, cap * sizeof(float4)));
@@ -687,7 +741,8 @@ void bn_scene_destroy(BnScene* s) {
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
-  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list, (void*)s->counters, (void*)s->shadow_ref, (void*)s->film})
+  release_wave_buffers(s);
+  for (void* p : {(void*)s->counters, (void*)s->shadow_ref, (void*)s->film})
     if (p) cudaFree(p);
   delete s;
 }
