@@ -290,10 +290,17 @@ def main():
         b_sh = algorithmic_bytes_per_ray(cst["shadow_counters"], B_IO_SHADOW)
         ext_s = tot["extend_ms"] * 1e-3
         achieved = tot["extend"] * b_ext / ext_s / 1e9 if ext_s > 0 else None
-        roofline = {"bound": "hbm", "kernel": "k_extend (closest-hit TLAS+BLAS traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and args.workload == "C2":
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        n_ext_launches = max(1, launches_total // (2 + 5 * MAX_DEPTH) * MAX_DEPTH)   # launches per wave = 2 + 5*maxDepth, maxDepth of them are extends
+        roofline = {"bound": "hbm", "kernel": "k_traverse<closest> (extend: TLAS+BLAS closest-hit traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": tot["extend"] * b_ext / n_ext_launches, "avg_launch_ms": tot["extend_ms"] / n_ext_launches,
                     "algorithmic_bytes_per_ray": b_ext, "algorithmic_bytes_per_ray_cap152": algorithmic_bytes_per_ray(cst["extend_counters"], B_IO_EXTEND, cap=True),
-                    "rays_per_launch": tot["extend"] / max(1, launches_total // 26 * 8), "rays_per_s": tot["extend"] / ext_s if ext_s > 0 else None,
+                    "rays_per_launch": tot["extend"] / n_ext_launches, "rays_per_s": tot["extend"] / ext_s if ext_s > 0 else None,
                     "kernel_share_of_step": tot["extend_ms"] / tot["render_ms"] if tot["render_ms"] else None,
                     "shadow": {"algorithmic_bytes_per_ray": b_sh, "achieved": (tot["shadow"] * b_sh / (tot["shadow_ms"] * 1e-3) / 1e9) if tot["shadow_ms"] else None,
                                "rays_per_s": tot["shadow"] / (tot["shadow_ms"] * 1e-3) if tot["shadow_ms"] else None},
