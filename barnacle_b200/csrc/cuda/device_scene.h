@@ -62,7 +62,7 @@ struct __align__(16) GInstTrav {
   uint32_t tri_base;                  // mesh's first GTri
   uint32_t is_sphere;
   float radius;
-  uint32_t pad;
+  uint32_t identity;                  // mesh instance whose ObjectToWorld AND WorldToObject are exactly the identity
 };
 static_assert(sizeof(GInstTrav) == 96, "GInstTrav must be 96 B");
 

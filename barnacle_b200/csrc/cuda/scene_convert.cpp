@@ -222,6 +222,16 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       const bn::GMesh& gm = out.meshes[in.prim_id];
       std::memcpy(tv.bmin, gm.tree.bmin, 12); std::memcpy(tv.bmax, gm.tree.bmax, 12);
       tv.root = gm.tree.root; tv.node_base = gm.tree.node_base; tv.tri_base = gm.tri_base;
+      // Identity instances (e.g. the Cornell-box walls): Vector3.Transform by I returns its argument
+      // bit for bit for the rays the fast path takes (no zero direction component; the sign of a
+      // zero in the origin cannot reach a result), and the BLAS root box IS the instance's world
+      // box, already tested.  The traversal then skips the transform, the reciprocal and that test.
+      static const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+      const bool same_box = std::memcmp(in.bounds_min, gm.tree.bmin, 12) == 0 && std::memcmp(in.bounds_max, gm.tree.bmax, 12) == 0;
+      bool ident = same_box;
+      for (int k = 0; k < 16; ++k)  // numeric compare: a -0.0 entry (Matrix4x4.Invert produces them) acts like +0.0 here
+        ident = ident && in.object_to_world[k] == kIdentity[k] && in.world_to_object[k] == kIdentity[k];
+      tv.identity = ident ? 1u : 0u;
       // MeshInstance.EvalPDF (Mesh.fs:300-304) for tag = 0:
       // Table[0].pdf / SurfaceArea(Transform(triangle 0, ObjectToWorld))
       const BnMesh& mm = d.meshes[in.prim_id];

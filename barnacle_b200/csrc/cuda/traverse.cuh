@@ -345,11 +345,20 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
       if (isE) {
         const uint32_t slot = cur & kIndexMask;
         const float4* ip = reinterpret_cast<const float4*>(sc.inst_trav + slot);
+        const float4 m0 = __ldg(ip + 3), m2 = __ldg(ip + 5);
+        tri_k = 0;
+        if (fbits(m2.w)) {
+          // identity mesh instance: object space == world space, root box == instance box (passed)
+          o = wo; d = wd; inv = winv; signs = wsigns;
+          in_obj = true;
+          cur_inst = (int)slot;
+          cur = fbits(m0.w);
+          continue;
+        }
         const Mat43 M = load_mat43(ip);
-        const float4 m0 = __ldg(ip + 3), m1 = __ldg(ip + 4), m2 = __ldg(ip + 5);
+        const float4 m1 = __ldg(ip + 4);
         const float3 oo = transform_point(wo, M);  // Ray.Transform (Ray.fs:19-22)
         const float3 od = transform_dir(wd, M);
-        tri_k = 0;
         if (fbits(m2.y)) {
           float tp;
           const int root = sphere_test(m2.z, oo, od, t, tp);

@@ -201,7 +201,7 @@ def main():
     clocks = ClockSampler(local) if rank == 0 else None
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot = {"extend": 0, "shadow": 0, "paths": 0, "launches": 0, "extend_ms": 0.0, "shade_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0}
+    tot = {"extend": 0, "shadow": 0, "paths": 0, "launches": 0, "my_launches": 0, "extend_ms": 0.0, "shade_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0}
     step_ms = []
     barrier()
     for _ in range(args.steps):
@@ -295,7 +295,7 @@ def main():
         if os.path.exists(tpath) and args.workload == "C2":
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-        n_ext_launches = max(1, launches_total // (2 + 5 * MAX_DEPTH) * MAX_DEPTH)   # launches per wave = 2 + 5*maxDepth, maxDepth of them are extends
+        n_ext_launches = max(1, tot["launches"] // (2 + 5 * MAX_DEPTH) * MAX_DEPTH)   # launches per wave = 2 + 5*maxDepth, maxDepth of them are extends
         roofline = {"bound": "hbm", "kernel": "k_traverse<closest> (extend: TLAS+BLAS closest-hit traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": tot["extend"] * b_ext / n_ext_launches, "avg_launch_ms": tot["extend_ms"] / n_ext_launches,
@@ -320,7 +320,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": label, "max_depth": MAX_DEPTH, "rr_depth": RR_DEPTH, "parallelism": f"sample-split x{world} + film reduce" if world > 1 else "single GPU",
-                       "l2_flush": "256 MiB memset between steps", "wave_paths": int(os.environ.get("BN_WAVE_PATHS", 4 << 20))},
+                       "l2_flush": "256 MiB memset between steps", "wave_paths": int(os.environ.get("BN_WAVE_PATHS", 16 << 20))},
             "samples_per_s": paths_total / (total_ms * 1e-3),
             "rays_per_step": rays_total / args.steps, "paths_per_step": paths_total / args.steps,
             "gpu_launches": launches_total,
