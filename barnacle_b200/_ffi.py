@@ -17,6 +17,7 @@ BN_ERR_INVALID, BN_ERR_CUDA, BN_ERR_NO_DEVICE, BN_ERR_IO, BN_ERR_NO_LIGHT = -1, 
 BN_PRIM_MESH, BN_PRIM_SPHERE = 0, 1
 BN_MAT_LAMBERTIAN, BN_MAT_MIRROR, BN_MAT_DIELECTRIC, BN_MAT_PBR = 0, 1, 2, 3
 BN_CAM_PINHOLE, BN_CAM_THIN_LENS = 0, 1
+BN_INTEGRATOR_PATH_TRACING, BN_INTEGRATOR_DIRECT, BN_INTEGRATOR_NORMAL = 0, 1, 2
 BN_RENDER_TRACE_NULL_SHADOW = 1
 BN_RENDER_PROFILE = 2
 BN_RENDER_FORCE_EXACT = 4
@@ -75,7 +76,7 @@ class BnRenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_depth", C.c_int32),
                 ("rr_depth", C.c_int32), ("frame_id", C.c_int32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32),
                 ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32), ("flags", C.c_uint32),
-                ("interleave_count", C.c_int32), ("interleave_index", C.c_int32)]
+                ("interleave_count", C.c_int32), ("interleave_index", C.c_int32), ("integrator", C.c_int32)]
 
 
 class BnStats(C.Structure):
@@ -112,6 +113,7 @@ SYMBOLS = {
     "bn_trace": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int, _VP]),
     "bn_trace_device": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int, _VP, _VP, C.POINTER(C.c_float)]),
     "bn_render_radiance": (C.c_int, [_VP, C.POINTER(BnRenderParams), _VP]),
+    "bn_film_to_rgba8_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
     "bn_host_scene_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(_VP)]),
     "bn_host_scene_load_string": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(_VP)]),
     "bn_host_scene_desc": (C.POINTER(BnSceneDesc), [_VP]),

@@ -34,8 +34,13 @@ int main(int argc, char** argv) {
   std::printf("Loaded scene from %s\n", input.c_str());
   BnHostSceneInfo info{};
   bn_host_scene_info(host, &info);
-  if (info.integrator != 2) {
-    std::fprintf(stderr, "integrator type %d is outside the GPU hot path (path-tracing only)\n", info.integrator);
+  // Loader.fs:185-188 order (normal, direct, path-tracing, pssmlt) -> BN_INTEGRATOR_*
+  int integrator;
+  if (info.integrator == 2) integrator = BN_INTEGRATOR_PATH_TRACING;
+  else if (info.integrator == 1) integrator = BN_INTEGRATOR_DIRECT;
+  else if (info.integrator == 0) integrator = BN_INTEGRATOR_NORMAL;
+  else {
+    std::fprintf(stderr, "integrator type %d (pssmlt) is outside the GPU hot path\n", info.integrator);
     return 3;
   }
   BnScene* scene = nullptr;
@@ -44,6 +49,7 @@ int main(int argc, char** argv) {
   p.width = info.width; p.height = info.height; p.spp = info.spp; p.max_depth = info.max_depth; p.rr_depth = info.rr_depth;
   p.sample_begin = 0; p.sample_end = info.spp; p.x0 = 0; p.y0 = 0; p.x1 = info.width; p.y1 = info.height;
   p.interleave_count = 1;
+  p.integrator = integrator;
   std::vector<float> film((size_t)info.width * info.height * 3);
   BnStats st{};
   auto t0 = std::chrono::steady_clock::now();

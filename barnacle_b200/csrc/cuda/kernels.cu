@@ -60,6 +60,7 @@ struct WaveParams {
   uint32_t flags;
   float inv_spp;
   int il_count, il_index;  // tile-row interleave (BnRenderParams.interleave_*)
+  int integrator;          // BN_INTEGRATOR_*
 };
 
 // ---- warp helpers --------------------------------------------------------------
@@ -208,7 +209,16 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
         P = transform_point(pobj, O2W);
         const Onb onb = transform_onb(onb_from_n(nobj), O2W);
 
-        if (light >= 0) {  // PathTracing.fs:30-40 + UniformLightSampler.Eval (Uniform.fs:40-49)
+        if (wp.integrator == BN_INTEGRATOR_NORMAL) {  // NormalIntegrator.Li (Normal.fs:10-17)
+          const float3 c = 0.5f * (onb.n + splat(1.f));
+          rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
+        } else if (wp.integrator == BN_INTEGRATOR_DIRECT && bounce == 0) {
+          if (light >= 0) {  // Direct.fs:16-17: L + EvalEmit(-ray.Direction)
+            const float3 Le = light_eval(load_light(sc, light), dot(-d, onb.n));
+            const float4 L4 = rad[pid];
+            rad[pid] = make_float4(L4.x + Le.x, L4.y + Le.y, L4.z + Le.z, 0.f);
+          }
+        } else if (light >= 0) {  // PathTracing.fs:30-40 + UniformLightSampler.Eval (Uniform.fs:40-49)
           const float3 wo = normalize(o - P);
           const float cos_wo = dot(onb.n, wo);
           float pdf_surface;
@@ -222,23 +232,26 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
           const float dist2 = length_sq(o - P);
           const float3 Le = light_eval(load_light(sc, light), dot(wo, onb.n));
           const float lpdf = dist2 * pdf_surface / (net_max(fabsf(cos_wo), 1e-6f) * (float)sc.n_light_inst);
-          const float w = bounce == 0 ? 1.f : prev_pdf * (1.f / (lpdf + prev_pdf));
+          // PathTracing.fs:33-38 MIS weight | Direct.fs:36-38: bsdf * L * (1 / lightPdf), no MIS
+          const float w = wp.integrator == BN_INTEGRATOR_DIRECT ? (1.f / lpdf) : (bounce == 0 ? 1.f : prev_pdf * (1.f / (lpdf + prev_pdf)));
           const float4 L4 = rad[pid];
           const float3 L = vfma(beta, Le * w, f3(L4.x, L4.y, L4.z));
           rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
         }
-        if (material >= 0) {
+        const bool scatter = wp.integrator == BN_INTEGRATOR_PATH_TRACING || (wp.integrator == BN_INTEGRATOR_DIRECT && bounce == 0);
+        if (material >= 0 && scatter) {
+          const bool direct = wp.integrator == BN_INTEGRATOR_DIRECT;
           const GMaterial mat = load_material(sc, material);
           const float usel = lcg(rng);
           const float ulx = lcg(rng), uly = lcg(rng);
           const LightSampleRec ls = light_sampler_sample(sc, P, usel, ulx, uly);  // PathTracing.fs:43
           const float dist = length(ls.p - P);
           const float3 wo_l = world_to_local(onb, -d);
-          if (ls.pdf != 0.f) {  // :47-59
+          if (direct || ls.pdf != 0.f) {  // PathTracing.fs:47-59 | Direct.fs:25-29 traces whatever the pdf
             ref_shadow = true;
             const BsdfEval fe = material_eval(mat, wo_l, world_to_local(onb, ls.wi));
-            sh_a = beta * fe.bsdf;
-            sh_b = ls.L * (1.f / (fe.pdf + ls.pdf));
+            sh_a = direct ? fe.bsdf : beta * fe.bsdf;
+            sh_b = ls.L * (1.f / (direct ? ls.pdf : fe.pdf + ls.pdf));
             // fma(0, finite, L) == L bit for bit: the connection cannot change the image
             const bool null_contrib = sh_a.x == 0.f && sh_a.y == 0.f && sh_a.z == 0.f && isfinite(sh_b.x) && isfinite(sh_b.y) && isfinite(sh_b.z);
             has_shadow = !null_contrib || (wp.flags & BN_RENDER_TRACE_NULL_SHADOW);
@@ -248,7 +261,12 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
           const float ulobe = lcg(rng);
           const float ubx = lcg(rng), uby = lcg(rng);
           const BsdfSample bs = material_sample(mat, wo_l, ulobe, ubx, uby);  // :61
-          if (bs.eval.pdf != 0.f) {
+          if (direct) {  // Direct.fs:31-38: the sampled direction is followed whatever its pdf; its weight is bsdf alone
+            nd = local_to_world(onb, bs.wi);
+            beta = bs.eval.bsdf;
+            bs_pdf = bs.eval.pdf;
+            alive = true;
+          } else if (bs.eval.pdf != 0.f) {
             nd = local_to_world(onb, bs.wi);
             beta = beta * bs.eval.bsdf * (1.f / bs.eval.pdf);
             bs_pdf = bs.eval.pdf;
@@ -326,6 +344,21 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(WaveParams wp, const floa
       acc = vfma(splat(wp.inv_spp), radiance, acc);
     }
     px[0] = acc.x; px[1] = acc.y; px[2] = acc.z;
+  }
+}
+
+// Film.PostProcess + Rgba32 (Film.fs:21-30,64): ACES / gamma / identity, clamp, 8-bit RGBA
+__global__ void __launch_bounds__(256) k_film_to_rgba8(const float* __restrict__ film, size_t npix, int tone, uchar4* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float x = film[i * 3 + k];
+      if (tone == 1) x = x * (2.51f * x + 0.03f) / (x * (2.43f * x + 0.59f) + 0.14f);
+      else if (tone == 2) x = powf(x, 1.f / 2.2f);
+      c[k] = !(x > 0.f) ? 0.f : (x > 1.f ? 1.f : x);  // Vector3.Clamp; NaN -> 0
+    }
+    out[i] = make_uchar4((unsigned char)(c[0] * 255.f + 0.5f), (unsigned char)(c[1] * 255.f + 0.5f), (unsigned char)(c[2] * 255.f + 0.5f), 255);
   }
 }
 
@@ -515,7 +548,8 @@ int ensure_wave_buffers(BnScene* s, size_t cap) {
 int validate_params(const BnRenderParams* p) {
   if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth < 0 || p->sample_begin < 0 || p->sample_end > p->spp ||
       p->sample_begin > p->sample_end || p->x0 < 0 || p->y0 < 0 || p->x1 > p->width || p->y1 > p->height || p->x0 > p->x1 || p->y0 > p->y1 ||
-      (p->interleave_count > 1 && (p->interleave_index < 0 || p->interleave_index >= p->interleave_count))) {
+      (p->interleave_count > 1 && (p->interleave_index < 0 || p->interleave_index >= p->interleave_count)) ||
+      p->integrator < BN_INTEGRATOR_PATH_TRACING || p->integrator > BN_INTEGRATOR_NORMAL) {
     bnhost::set_error("bn_render: invalid BnRenderParams");
     return BN_ERR_INVALID;
   }
@@ -542,7 +576,9 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
   BN_CUDA(cudaEventRecord(ev0, stream));
   uint64_t n_paths = 0;
   std::vector<int> h_counters;
-  if (total_blocks > 0 && ns > 0 && p->max_depth > 0) {
+  // bounces per path: PathTracing maxDepth | Direct: the hit and one BSDF-sampled ray | Normal: the hit
+  const int D_bounces = p->integrator == BN_INTEGRATOR_DIRECT ? 2 : (p->integrator == BN_INTEGRATOR_NORMAL ? 1 : p->max_depth);
+  if (total_blocks > 0 && ns > 0 && D_bounces > 0) {
     const size_t cap_target = wave_capacity_paths();
     long long blocks_per_wave = std::min<long long>(total_blocks, std::max<long long>(1, (long long)(cap_target / 32)));
     int samples_per_wave = (int)std::max<long long>(1, std::min<long long>(ns, (long long)cap_target / (blocks_per_wave * 32)));
@@ -553,7 +589,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     const long long n_sample_chunks = (ns + samples_per_wave - 1) / samples_per_wave;
     const long long n_waves = n_block_chunks * n_sample_chunks;
     // per wave: n_active(bounce 0..maxDepth) | n_shadow(bounce) | cursors 3 per bounce | deferred counts 2 per bounce
-    const int D = p->max_depth;
+    const int D = D_bounces;
     const size_t per_wave = (size_t)(D + 1) + D + 3 * (size_t)D + 2 * (size_t)D;
     const size_t need = per_wave * (size_t)n_waves;
     if (s->counters_len < need) {
@@ -593,7 +629,8 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     for (long long bc = 0; bc < n_block_chunks; ++bc) {
       for (long long scn = 0; scn < n_sample_chunks; ++scn, ++wave) {
         WaveParams wp{};
-        wp.width = p->width; wp.height = p->height; wp.spp = p->spp; wp.max_depth = p->max_depth; wp.rr_depth = p->rr_depth;
+        wp.width = p->width; wp.height = p->height; wp.spp = p->spp; wp.max_depth = D; wp.rr_depth = p->rr_depth;
+        wp.integrator = p->integrator;
         wp.frame_id = p->frame_id; wp.x0 = p->x0; wp.y0 = p->y0; wp.x1 = p->x1; wp.y1 = p->y1; wp.nbx = nbx;
         wp.block_begin = (int)(bc * blocks_per_wave);
         wp.n_blocks = (int)std::min<long long>(blocks_per_wave, total_blocks - bc * blocks_per_wave);
@@ -788,6 +825,16 @@ int bn_render_radiance(BnScene* s, const BnRenderParams* p, float* radiance) {
   if (rc == BN_OK && !cuda_ok(cudaMemcpy(radiance, d, len * sizeof(float), cudaMemcpyDeviceToHost), "copy radiance")) rc = BN_ERR_CUDA;
   cudaFree(d);
   return rc;
+}
+
+int bn_film_to_rgba8_device(BnScene* s, const void* d_film, int32_t w, int32_t h, int32_t tone, void* d_rgba8, void* stream_v) {
+  if (!s || !d_film || !d_rgba8 || w <= 0 || h <= 0 || tone < 0 || tone > 2) { bnhost::set_error("bn_film_to_rgba8_device: bad arguments"); return BN_ERR_INVALID; }
+  BN_CUDA(cudaSetDevice(s->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  k_film_to_rgba8<<<s->num_sms * 4, 256, 0, stream>>>(static_cast<const float*>(d_film), (size_t)w * h, tone, static_cast<uchar4*>(d_rgba8));
+  BN_CUDA(cudaGetLastError());
+  BN_CUDA(cudaStreamSynchronize(stream));
+  return BN_OK;
 }
 
 int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, void* d_hits, void* stream_v, float* ms) {

@@ -51,7 +51,7 @@ def partition(width: int, height: int, spp: int, world: int, rank: int, mode: st
 def shard_params(base: BnRenderParams, shard: Shard) -> BnRenderParams:
     return BnRenderParams(base.width, base.height, base.spp, base.max_depth, base.rr_depth, base.frame_id,
                           shard.sample_begin, shard.sample_end, base.x0, base.y0, base.x1, base.y1, base.flags,
-                          shard.interleave_count, shard.interleave_index)
+                          shard.interleave_count, shard.interleave_index, base.integrator)
 
 
 def owned_pixels(width: int, height: int, shard: Shard) -> int:

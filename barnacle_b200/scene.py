@@ -50,10 +50,10 @@ class RenderStats:
 
 
 def make_params(width, height, spp, max_depth=8, rr_depth=5, frame_id=0, sample_begin=0, sample_end=None,
-                rect=None, flags=0, interleave=(1, 0)) -> BnRenderParams:
+                rect=None, flags=0, interleave=(1, 0), integrator=0) -> BnRenderParams:
     x0, y0, x1, y1 = rect if rect is not None else (0, 0, width, height)
     return BnRenderParams(width, height, spp, max_depth, rr_depth, frame_id, sample_begin,
-                          spp if sample_end is None else sample_end, x0, y0, x1, y1, flags, interleave[0], interleave[1])
+                          spp if sample_end is None else sample_end, x0, y0, x1, y1, flags, interleave[0], interleave[1], integrator)
 
 
 class Film:
@@ -147,15 +147,20 @@ class GpuScene:
 
 class GpuPathTracingIntegrator:
     """Drop-in for PathTracingIntegrator (PathTracing.fs:9-12) whose Render
-    (Integrator.fs:46-55) runs on the GPU."""
+    (Integrator.fs:46-55) runs on the GPU.  `kind` selects the Li variant:
+    "path-tracing" | "direct" (Direct.fs) | "normal" (Normal.fs)."""
 
-    def __init__(self, spp: int, max_depth: int = 8, rr_depth: int = 5):
+    KINDS = {"path-tracing": _ffi.BN_INTEGRATOR_PATH_TRACING, "direct": _ffi.BN_INTEGRATOR_DIRECT, "normal": _ffi.BN_INTEGRATOR_NORMAL}
+
+    def __init__(self, spp: int, max_depth: int = 8, rr_depth: int = 5, kind: str = "path-tracing"):
         self.SamplePerPixel, self.MaxDepth, self.RRDepth = spp, max_depth, rr_depth
+        self.kind = kind
         self.FrameId = 0
         self.last_stats: RenderStats | None = None
 
     def Render(self, gpu_scene: GpuScene, film: Film, flags: int = 0):
-        p = make_params(film.ImageWidth, film.ImageHeight, self.SamplePerPixel, self.MaxDepth, self.RRDepth, self.FrameId, flags=flags)
+        p = make_params(film.ImageWidth, film.ImageHeight, self.SamplePerPixel, self.MaxDepth, self.RRDepth, self.FrameId, flags=flags,
+                        integrator=self.KINDS[self.kind])
         _, self.last_stats = gpu_scene.render(p, film.Pixels)
         self.FrameId += 1
 
@@ -170,7 +175,8 @@ class Scene:
         self.info = info
         self.Film = Film(info.width, info.height, TONE_MAPPING[info.tone_mapping])
         self.integrator_type = INTEGRATORS[info.integrator]
-        self.Integrator = GpuPathTracingIntegrator(info.spp, info.max_depth, info.rr_depth)
+        kind = self.integrator_type if self.integrator_type in GpuPathTracingIntegrator.KINDS else "path-tracing"
+        self.Integrator = GpuPathTracingIntegrator(info.spp, info.max_depth, info.rr_depth, kind)
         self._gpu: GpuScene | None = None
 
     @staticmethod
@@ -209,8 +215,8 @@ class Scene:
     def Render(self, t: float, filename: str | None, device: int = 0) -> float:
         """Render.fs:10-19.  Returns the seconds spent in Integrator.Render (the
         reference's Stopwatch region)."""
-        if self.integrator_type != "path-tracing":
-            raise BarnacleError(f"integrator '{self.integrator_type}' is outside the GPU hot path (path-tracing only)")
+        if self.integrator_type not in GpuPathTracingIntegrator.KINDS:
+            raise BarnacleError(f"integrator '{self.integrator_type}' is outside the GPU hot path (path-tracing, direct, normal)")
         self.Film.Clear()
         gpu = self.gpu(device)
         t0 = time.perf_counter()

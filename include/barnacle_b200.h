@@ -152,7 +152,15 @@ typedef struct BnRenderParams {
    * rows r with r % interleave_count == interleave_index are rendered.
    * interleave_count <= 1 renders every row. */
   int32_t interleave_count, interleave_index;
+  /* which ProgressiveIntegrator.Li runs (Loader.fs:185-188): BN_INTEGRATOR_* ; 0 = path tracing */
+  int32_t integrator;
 } BnRenderParams;
+
+enum {
+  BN_INTEGRATOR_PATH_TRACING = 0, /* PathTracingIntegrator.Li, Extensions/Integrator/PathTracing.fs:14-81 */
+  BN_INTEGRATOR_DIRECT = 1,       /* DirectIntegrator.Li,      Extensions/Integrator/Direct.fs:10-40 (max_depth / rr_depth ignored) */
+  BN_INTEGRATOR_NORMAL = 2        /* NormalIntegrator.Li,      Extensions/Integrator/Normal.fs:10-17 */
+};
 
 enum {
   BN_RENDER_DEFAULT = 0,
@@ -228,6 +236,11 @@ BN_API int bn_trace(BnScene* scene, const BnRay* rays, uint64_t n, int any_hit, 
  * kernel's device time in *ms (may be NULL). */
 BN_API int bn_trace_device(BnScene* scene, const void* d_rays, uint64_t n, int any_hit,
                            void* d_hits, void* cuda_stream, float* ms);
+
+/* Film.PostProcess + Rgba32 conversion (Base/Film.fs:21-30,55-66) on the device: d_film_rgb
+ * (W*H*3 float, device) -> d_rgba8 (W*H*4 bytes, device).  tone_mapping: 0 identity, 1 aces, 2 gamma. */
+BN_API int bn_film_to_rgba8_device(BnScene* scene, const void* d_film_rgb, int32_t width, int32_t height, int32_t tone_mapping,
+                                   void* d_rgba8, void* cuda_stream);
 
 /* Per-path radiance dump for parity tests: Li * 1/pdf for every (pixel, sample)
  * in the window, laid out [sample - sample_begin][(y - y0)*(x1-x0) + (x - x0)][3],

@@ -798,6 +798,67 @@ V3 path_li(const Scene& s, Ray ray, Sampler& sampler, int max_depth, int rr_dept
   return L;
 }
 
+// ---- DirectIntegrator.Li — Direct.fs:10-40 (no MIS; the BSDF-sampled emitter hit is weighted by
+// 1/lightPdf as written; the shadow ray is traced whatever the light pdf; true divisions) ----------
+template <bool COUNT>
+V3 direct_li(const Scene& s, Ray ray, Sampler& sampler, PathStats& ps, Counters* ce, Counters* cs) {
+  float t = kInf;
+  Interaction it{};
+  V3 L{0, 0, 0};
+  ps.extend++;
+  if (!scene_closest<COUNT>(s, ray, it, t, ce)) return L;
+  const BnInstance& in = s.inst[it.inst];
+  if (in.light_id >= 0) L = L + light_eval(s.lights[in.light_id], dot(-ray.d, it.geom.onb.n));  // EvalEmit(-ray.Direction)
+  if (in.material_id < 0) return L;
+  const BnMaterial& mat = s.mats[in.material_id];
+  float usel = sampler.next1d();
+  V2 ul = sampler.next2d();
+  LightSample ls = light_sampler_sample(s, it.geom.p, usel, ul);
+  Ray shadow{it.geom.p, ls.wi};
+  float dist = length(ls.eval.p - it.geom.p);
+  V3 wo_l = world_to_local(it.geom.onb, -ray.d);
+  ps.shadow++;
+  if (COUNT) {
+    BSDFEval probe = material_eval(mat, wo_l, world_to_local(it.geom.onb, ls.wi));
+    V3 b = ls.eval.L * (1.f / ls.eval.pdf);
+    bool null_contrib = probe.bsdf.x == 0.f && probe.bsdf.y == 0.f && probe.bsdf.z == 0.f && std::isfinite(b.x) && std::isfinite(b.y) && std::isfinite(b.z);
+    if (!null_contrib) ps.shadow_nonnull++;
+  }
+  if (!scene_any<COUNT>(s, shadow, dist - 1e-3f, cs)) {
+    BSDFEval fe = material_eval(mat, wo_l, world_to_local(it.geom.onb, ls.wi));
+    L = vfma(fe.bsdf, ls.eval.L * (1.f / ls.eval.pdf), L);
+  }
+  float ulobe = sampler.next1d();
+  V2 ub = sampler.next2d();
+  BSDFSample bs = material_sample(mat, wo_l, ulobe, ub);
+  Ray next{it.geom.p, local_to_world(it.geom.onb, bs.wi)};
+  Interaction it2{};
+  t = kInf;
+  ps.extend++;
+  if (scene_closest<COUNT>(s, next, it2, t, ce) && s.inst[it2.inst].light_id >= 0) {
+    LightEval le = light_sampler_eval(s, next.o, it2);
+    L = vfma(bs.eval.bsdf, le.L * (1.f / le.pdf), L);
+  }
+  return L;
+}
+
+// ---- NormalIntegrator.Li — Normal.fs:10-17 ---------------------------------------------------------
+template <bool COUNT>
+V3 normal_li(const Scene& s, Ray ray, PathStats& ps, Counters* ce) {
+  float t = kInf;
+  Interaction it{};
+  ps.extend++;
+  if (scene_closest<COUNT>(s, ray, it, t, ce)) return 0.5f * (it.geom.onb.n + splat(1.f));
+  return {0, 0, 0};
+}
+
+template <bool COUNT>
+V3 integrator_li(const Scene& s, const BnRenderParams* p, const Ray& ray, Sampler& sp, PathStats& ps, Counters* ce, Counters* cs) {
+  if (p->integrator == BN_INTEGRATOR_DIRECT) return direct_li<COUNT>(s, ray, sp, ps, ce, cs);
+  if (p->integrator == BN_INTEGRATOR_NORMAL) return normal_li<COUNT>(s, ray, ps, ce);
+  return path_li<COUNT>(s, ray, sp, p->max_depth, p->rr_depth, ps, ce, cs);
+}
+
 }  // namespace
 
 // =============================================================================
@@ -926,7 +987,7 @@ BO_API int bo_render_radiance(const BoScene* sc, const BnRenderParams* p, float*
       V2 ul = sp.next2d();
       Ray ray = primary_ray(s.cam, p->width, p->height, x, y, up, ul);
       PathStats ps;
-      V3 L = path_li<false>(s, ray, sp, p->max_depth, p->rr_depth, ps, nullptr, nullptr) * (1.f / 1.f);
+      V3 L = integrator_li<false>(s, p, ray, sp, ps, nullptr, nullptr) * (1.f / 1.f);
       float* o = radiance + ((int64_t)(sm - p->sample_begin) * npix + i) * 3;
       o[0] = L.x; o[1] = L.y; o[2] = L.z;
     }
@@ -971,8 +1032,7 @@ BO_API int bo_render(const BoScene* sc, const BnRenderParams* p, float* film, ui
             V2 up = sp.next2d();
             V2 ul = sp.next2d();
             Ray ray = primary_ray(s.cam, W, H, x, y, up, ul);
-            V3 li = instrument ? path_li<true>(s, ray, sp, p->max_depth, p->rr_depth, ps, &ce, &cs)
-                               : path_li<false>(s, ray, sp, p->max_depth, p->rr_depth, ps, &ce, &cs);
+            V3 li = instrument ? integrator_li<true>(s, p, ray, sp, ps, &ce, &cs) : integrator_li<false>(s, p, ray, sp, ps, &ce, &cs);
             V3 radiance = li * (1.f / 1.f);  // camera pdf is 1 (Pinhole.fs:27)
             accum = vfma(splat(inv_spp), radiance, accum);
           }

@@ -128,6 +128,21 @@ def test_direct_lighting_estimate_converges(lib):
     assert abs(got / expect - 1) < 0.03, (got, expect)
 
 
+def test_normal_and_direct_integrators_on_micro_scene(lib):
+    """NormalIntegrator: 0.5*(n+1) (Normal.fs:15); DirectIntegrator on a bare emitter: its emission (Direct.fs:16-17)."""
+    from barnacle_b200 import _ffi
+    tr = [{"keyframes": [{"scale": [50, 1, 50], "rotation": [1.5707963267948966, 0, 0], "translation": [0, 0, -5]}]}]
+    s, o = load(scene_json([{"type": "quad"}], [{"primitive": 0, "light": 0}], [{"children": [1, 2]}, {"instances": [0], "transform": 0}, CAM_NODE],
+                           transforms=tr, lights=[{"type": "diffuse", "emission": [3.0, 2.0, 1.0]}]))
+    film, st = o.render(make_params(8, 8, 2, integrator=_ffi.BN_INTEGRATOR_DIRECT))
+    assert np.array_equal(film, np.tile(np.array([3, 2, 1], np.float32), (64, 1))) and st["shadow_rays"] == 0
+    film, st = o.render(make_params(8, 8, 2, integrator=_ffi.BN_INTEGRATOR_NORMAL))
+    hit, g = o.closest_geom(rays(((0, 0, 0), (0, 0, -1), np.inf)))
+    assert hit and np.allclose(np.abs(g[1]), [0, 0, 1], atol=1e-6)
+    np.testing.assert_allclose(film, np.tile(0.5 * (g[1] + 1), (64, 1)), atol=1e-6)
+    assert st["extend_rays"] == 8 * 8 * 2 and st["shadow_rays"] == 0
+
+
 def test_loader_errors_match_reference_messages(lib):
     from barnacle_b200._ffi import BarnacleError
     bad = json.loads(scene_json([{"type": "torus"}], [], [{}]))
