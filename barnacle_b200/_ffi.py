@@ -18,6 +18,7 @@ BN_PRIM_MESH, BN_PRIM_SPHERE = 0, 1
 BN_MAT_LAMBERTIAN, BN_MAT_MIRROR, BN_MAT_DIELECTRIC, BN_MAT_PBR = 0, 1, 2, 3
 BN_CAM_PINHOLE, BN_CAM_THIN_LENS = 0, 1
 BN_INTEGRATOR_PATH_TRACING, BN_INTEGRATOR_DIRECT, BN_INTEGRATOR_NORMAL = 0, 1, 2
+BN_MLT_GAUSSIAN, BN_MLT_KELEMEN = 0, 1
 BN_RENDER_TRACE_NULL_SHADOW = 1
 BN_RENDER_PROFILE = 2
 BN_RENDER_FORCE_EXACT = 4
@@ -95,7 +96,20 @@ class BnHit(C.Structure):
 
 class BnHostSceneInfo(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("tone_mapping", C.c_int32), ("integrator", C.c_int32),
-                ("spp", C.c_int32), ("max_depth", C.c_int32), ("rr_depth", C.c_int32)]
+                ("spp", C.c_int32), ("max_depth", C.c_int32), ("rr_depth", C.c_int32),
+                ("n_bootstrap", C.c_int32), ("n_chains", C.c_int32), ("mutation_strategy", C.c_int32), ("large_step_prob", C.c_float)]
+
+
+class BnMltParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mutations_per_pixel", C.c_int32), ("max_depth", C.c_int32),
+                ("rr_depth", C.c_int32), ("frame_id", C.c_int32), ("n_bootstrap", C.c_int32), ("n_chains", C.c_int32),
+                ("strategy", C.c_int32), ("p0", C.c_float), ("p1", C.c_float), ("large_step_prob", C.c_float),
+                ("chain_begin", C.c_int32), ("chain_end", C.c_int32)]
+
+
+class BnMltStats(C.Structure):
+    _fields_ = [("b", C.c_float), ("reserved", C.c_uint32), ("accepted", C.c_uint64), ("proposed", C.c_uint64), ("rays", C.c_uint64),
+                ("bootstrap_ms", C.c_double), ("chains_ms", C.c_double)]
 
 
 assert C.sizeof(BnBVHNode) == 32 and C.sizeof(BnAliasEntry) == 12 and C.sizeof(BnInstance) == 168
@@ -113,6 +127,9 @@ SYMBOLS = {
     "bn_trace": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int, _VP]),
     "bn_trace_device": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int, _VP, _VP, C.POINTER(C.c_float)]),
     "bn_render_radiance": (C.c_int, [_VP, C.POINTER(BnRenderParams), _VP]),
+    "bn_render_pssmlt": (C.c_int, [_VP, C.POINTER(BnMltParams), _VP, C.POINTER(BnMltStats)]),
+    "bn_render_pssmlt_device": (C.c_int, [_VP, C.POINTER(BnMltParams), _VP, _VP, C.POINTER(BnMltStats)]),
+    "bn_pssmlt_bootstrap": (C.c_int, [_VP, C.POINTER(BnMltParams), _VP]),
     "bn_film_to_rgba8_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
     "bn_host_scene_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(_VP)]),
     "bn_host_scene_load_string": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(_VP)]),

@@ -429,26 +429,7 @@ struct TraceIO {
 // =================================================================================
 using namespace bn;
 
-struct BnScene {
-  int device = 0;
-  int num_sms = 0;
-  DScene d{};
-  std::vector<void*> allocs;
-  // wave buffers
-  size_t cap = 0;
-  float4* state[2] = {nullptr, nullptr};  // 3 planes each
-  float4* hits = nullptr;
-  float4* shq = nullptr;                  // 4 planes
-  float4* rad = nullptr;
-  int* defer_list = nullptr;              // rays deferred to the exact fix-up kernel (cap entries)
-  int* counters = nullptr;
-  size_t counters_len = 0;
-  unsigned long long* shadow_ref = nullptr;
-  float* film = nullptr;
-  size_t film_len = 0;
-  bool poisoned = false;
-  std::vector<cudaEvent_t> events;  // BN_RENDER_PROFILE: start/stop pairs, one per kernel launch
-};
+#include "scene_internal.h"
 
 namespace {
 

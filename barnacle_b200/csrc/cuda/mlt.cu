@@ -1,0 +1,507 @@
+// PSSMLT on the GPU ("next" row N1): PSSMLTIntegrator.Render, Extensions/Integrator/PSSMLT.fs:379-414.
+//
+// Phase 1 (bootstrap, :247-273) is embarrassingly parallel: one thread per bootstrap path.
+// Phase 2 (chains, :275-377) is a set of sequential Markov chains: one thread per chain, the
+// whole mutate -> trace -> accept/reject loop inside the thread ("megakernel"), film splats as
+// atomic adds (the reference's Film.Accumulate is a racy read-modify-write).
+// Parallelism is therefore the chain count: the reference's default of 1024 chains leaves a
+// B200 mostly idle; scenes meant for the GPU should ask for >= 10^5 chains (`n-chains`).
+// Every ray goes through trace_exact (the op-for-op traversal), every transcendental through
+// include/bn_portable_math.h, so a chain evolves bit-identically to the oracle's.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../../include/barnacle_b200.h"
+#include "scene_internal.h"
+#include "shade.cuh"
+#include "traverse.cuh"
+#include "vecmath.cuh"
+
+namespace bnhost {
+void set_error(const std::string& msg);
+}
+
+namespace bn {
+
+struct MltParams {
+  int width, height, max_depth, rr_depth, frame_id, n_bootstrap, n_chains, strategy;
+  float p0, p1, large_step_prob;
+  int chain_begin, chain_end, mutation_per_chain;
+  float inv_eff, inv_b;
+  int n_threads;   // stride of the primary-sample arrays
+  int xs_len;      // 4 + 7 * max_depth
+};
+
+// PrimarySample arrays, one column per thread (coalesced): value, backup, lastMod, modBackup
+struct MltState {
+  float* value;
+  float* backup;
+  int* last_mod;
+  int* mod_backup;
+};
+
+struct MltSampler {  // PSSMLT.fs:35-150
+  uint32_t inner;    // Sampler.state
+  bool large_step;
+  int last_large_step_iteration, current_iteration, sample_index, initialized;
+};
+
+BN_DEV float erf_inv(float x) {  // PSSMLT.fs:68-96
+  x = net_min(net_max(x, -0.99999f), 0.99999f);
+  float w = -bn_logf(__fmaf_rn(x, -x, 1.f));
+  if (w < 5.f) {
+    w = w - 2.5f;
+    float p = 2.81022636e-08f;
+    p = __fmaf_rn(p, w, 3.43273939e-07f);
+    p = __fmaf_rn(p, w, -3.5233877e-06f);
+    p = __fmaf_rn(p, w, -4.39150654e-06f);
+    p = __fmaf_rn(p, w, 0.00021858087f);
+    p = __fmaf_rn(p, w, -0.00125372503f);
+    p = __fmaf_rn(p, w, -0.00417768164f);
+    p = __fmaf_rn(p, w, 0.246640727f);
+    return __fmaf_rn(p, w, 1.50140941f) * x;
+  }
+  w = __fsqrt_rn(w) - 3.f;
+  float p = -0.000200214257f;
+  p = __fmaf_rn(p, w, 0.000100950558f);
+  p = __fmaf_rn(p, w, 0.00134934322f);
+  p = __fmaf_rn(p, w, -0.00367342844f);
+  p = __fmaf_rn(p, w, 0.00573950773f);
+  p = __fmaf_rn(p, w, -0.0076224613f);
+  p = __fmaf_rn(p, w, 0.00943887047f);
+  p = __fmaf_rn(p, w, 1.00167406f);
+  return __fmaf_rn(p, w, 2.83297682f) * x;
+}
+
+struct MltCtx {
+  const MltParams& p;
+  const MltState& st;
+  int tid;
+  MltSampler m;
+
+  BN_DEV void init(uint32_t seed_state) {
+    m.inner = seed_state; m.large_step = false;
+    m.last_large_step_iteration = 0; m.current_iteration = 0; m.sample_index = 0; m.initialized = 0;
+  }
+  BN_DEV void start_iteration() {  // :57-60
+    m.large_step = m.current_iteration == 0 || lcg(m.inner) < p.large_step_prob;
+    m.current_iteration++;
+    m.sample_index = 0;
+  }
+  BN_DEV float next1d() {  // EnsureReady(GetNextIndex()), :62-138
+    const int index = m.sample_index++;
+    const size_t at = (size_t)index * p.n_threads + tid;
+    float value;
+    int last_mod;
+    if (m.initialized <= index) { value = 0.f; last_mod = 0; m.initialized = index + 1; }
+    else { value = st.value[at]; last_mod = st.last_mod[at]; }
+    if (last_mod < m.last_large_step_iteration) { value = lcg(m.inner); last_mod = m.last_large_step_iteration; }
+    st.backup[at] = value; st.mod_backup[at] = last_mod;  // BackUp
+    float v;
+    if (m.large_step) {
+      v = lcg(m.inner);
+    } else if (p.strategy == BN_MLT_GAUSSIAN) {
+      const float normal_sample = __fsqrt_rn(2.f) * erf_inv(__fmaf_rn(2.f, lcg(m.inner), -1.f));
+      const float effective_sigma = p.p0 * __fsqrt_rn((float)(m.current_iteration - last_mod));
+      v = __fmaf_rn(normal_sample, effective_sigma, value);
+    } else {  // Kelemen(epsMin = p0, epsMax = p1)
+      v = value;
+      const float a = bn_logf(p.p1 / p.p0);
+      for (int k = last_mod; k <= m.current_iteration - 1; ++k) {
+        const float u1 = lcg(m.inner) - 0.5f;
+        const float u2 = u1 < 0.f ? 1.f + 2.f * u1 : 2.f * u1;
+        v = v + copysignf(p.p1 * bn_expf(-a * u2), u1);
+      }
+    }
+    v = v - floorf(v);
+    st.value[at] = v; st.last_mod[at] = m.current_iteration;
+    return v;
+  }
+  BN_DEV void reject() {  // :142-146
+    for (int i = 0; i < m.initialized; ++i) {
+      const size_t at = (size_t)i * p.n_threads + tid;
+      st.value[at] = st.backup[at]; st.last_mod[at] = st.mod_backup[at];
+    }
+    m.current_iteration--;
+  }
+  BN_DEV void accept() { if (m.large_step) m.last_large_step_iteration = m.current_iteration; }
+};
+
+// Interaction of a closest hit, rebuilt as the intersection routines produce it
+// (same code path as k_shade; Primitive.fs:57-58, Mesh.fs:76-78, Sphere.fs:50-75).
+struct Surface {
+  float3 P;
+  Onb onb;
+  int material, light;
+  bool is_sphere;
+  float aux;  // mesh: MeshInstance.EvalPDF for tag 0 | sphere: radius
+  Mat43 W2O;
+};
+BN_DEV Surface rebuild_surface(const DScene& sc, float3 o, float3 d, const TraceResult& h) {
+  Surface s;
+  const float4* hp = reinterpret_cast<const float4*>(sc.inst_head + h.inst);
+  const float4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
+  const uint32_t kind_prim = __float_as_uint(h0.w);
+  s.material = __float_as_int(h1.w); s.light = __float_as_int(h2.x); s.aux = h2.y;
+  s.W2O = load_mat43(reinterpret_cast<const float4*>(sc.inst_w2o + h.inst));
+  const Mat43 O2W = load_mat43(reinterpret_cast<const float4*>(sc.inst_o2w + h.inst));
+  const float3 oo = transform_point(o, s.W2O), od = transform_dir(d, s.W2O);
+  const float3 pobj = point_at(oo, od, h.t);
+  float3 nobj;
+  s.is_sphere = (kind_prim & 0x80000000u) != 0u;
+  if (s.is_sphere) {
+    nobj = normalize(pobj);
+    if (h.prim == 0 && dot(nobj, od) > 0.f) nobj = -nobj;
+  } else {
+    float3 p0, p1, p2;
+    load_tri(sc.tris + h.prim, p0, p1, p2);
+    nobj = normalize(cross(p1 - p0, p2 - p0));
+  }
+  s.P = transform_point(pobj, O2W);
+  s.onb = transform_onb(onb_from_n(nobj), O2W);
+  return s;
+}
+
+// PSSMLTIntegrator.Li — PSSMLT.fs:172-245 (fixed 7 dimensions per bounce)
+BN_DEV float3 mlt_li(const DScene& sc, float3 o, float3 d, MltCtx& ctx, unsigned long long& rays) {
+  const MltParams& p = ctx.p;
+  float3 L = splat(0.f), beta = splat(1.f);
+  float prev_pdf = 0.f;
+  int depth = 0;
+  while (depth < p.max_depth) {
+    TraceResult h;
+    trace_exact<false>(sc, o, d, CUDART_INF_F, h);
+    ++rays;
+    if (!h.hit) break;
+    const Surface sf = rebuild_surface(sc, o, d, h);
+    if (sf.light >= 0) {  // :187-198 + UniformLightSampler.Eval
+      const float3 wo = normalize(o - sf.P);
+      const float cos_wo = dot(sf.onb.n, wo);
+      float pdf_surface = sf.aux;
+      if (sf.is_sphere) {
+        const float j = length(cross(transform_dir(sf.onb.t, sf.W2O), transform_dir(sf.onb.b, sf.W2O)));
+        pdf_surface = j / (4.f * kPi * sf.aux * sf.aux);
+      }
+      const float dist2 = length_sq(o - sf.P);
+      const float3 Le = light_eval(load_light(sc, sf.light), dot(wo, sf.onb.n));
+      const float lpdf = dist2 * pdf_surface / (net_max(fabsf(cos_wo), 1e-6f) * (float)sc.n_light_inst);
+      const float w = depth == 0 ? 1.f : prev_pdf * (1.f / (lpdf + prev_pdf));
+      L = vfma(beta, Le * w, L);
+    }
+    const float u_light = ctx.next1d();
+    const float u_emit_x = ctx.next1d(), u_emit_y = ctx.next1d();
+    const float u_lobe = ctx.next1d();
+    const float u_bsdf_x = ctx.next1d(), u_bsdf_y = ctx.next1d();
+    const float u_rr = ctx.next1d();
+    if (sf.material < 0) break;
+    const GMaterial mat = load_material(sc, sf.material);
+    const LightSampleRec ls = light_sampler_sample(sc, sf.P, u_light, u_emit_x, u_emit_y);
+    const float dist = length(ls.p - sf.P);
+    const float3 wo_l = world_to_local(sf.onb, -d);
+    if (ls.pdf != 0.f) {
+      TraceResult sh;
+      trace_exact<true>(sc, sf.P, ls.wi, dist - 1e-3f, sh);
+      ++rays;
+      if (!sh.hit) {
+        const BsdfEval fe = material_eval(mat, wo_l, world_to_local(sf.onb, ls.wi));
+        L = vfma(beta * fe.bsdf, ls.L * (1.f / (fe.pdf + ls.pdf)), L);
+      }
+    }
+    const BsdfSample bs = material_sample(mat, wo_l, u_lobe, u_bsdf_x, u_bsdf_y);
+    prev_pdf = bs.eval.pdf;
+    if (bs.eval.pdf == 0.f) break;
+    o = sf.P;
+    d = local_to_world(sf.onb, bs.wi);
+    beta = beta * bs.eval.bsdf * (1.f / bs.eval.pdf);
+    if (depth >= p.rr_depth) {
+      const float q = net_min(1.f, net_max(beta.x, net_max(beta.y, beta.z)));
+      if (u_rr < q) beta = beta * (1.f / q);
+      else break;
+    }
+    depth++;
+  }
+  return L;
+}
+
+BN_DEV float luminance(float3 L) { return dot(L, f3(0.2126f, 0.7152f, 0.0722f)); }
+
+// pixel from two primary samples, camera ray from two more, Li (PSSMLT.fs:254-269 / 284-300 / 332-349)
+BN_DEV float3 mlt_sample_path(const DScene& sc, MltCtx& ctx, int& px, int& py, unsigned long long& rays) {
+  const MltParams& p = ctx.p;
+  const float ux = ctx.next1d(), uy = ctx.next1d();
+  const float upx = ux * (float)p.width, upy = uy * (float)p.height;
+  px = min(p.width - 1, (int)upx);
+  py = min(p.height - 1, (int)upy);
+  const float ulx = ctx.next1d(), uly = ctx.next1d();
+  float3 o, d;
+  primary_ray(sc.cam, p.width, p.height, px, py, upx - (float)px, upy - (float)py, ulx, uly, o, d);
+  return mlt_li(sc, o, d, ctx, rays) * (1.f / 1.f);
+}
+
+BN_DEV uint32_t xxhash32_two(uint32_t x, uint32_t y) {  // Hash.fs:6-15
+  const uint32_t p2 = 2246822519u, p3 = 3266489917u, p4 = 668265263u, p5 = 374761393u;
+  uint32_t h = y + p5 + x * p3;
+  h = p4 * rotl17(h);
+  h = p2 * (h ^ (h >> 15));
+  h = p3 * (h ^ (h >> 13));
+  return h ^ (h >> 16);
+}
+
+__global__ void __launch_bounds__(128) k_mlt_bootstrap(DScene sc, MltParams p, MltState st, float* __restrict__ weights, unsigned long long* ray_count) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long rays = 0;
+  for (int id = tid; id < p.n_bootstrap; id += p.n_threads) {
+    MltCtx ctx{p, st, tid, {}};
+    ctx.init(xxhash32_two((uint32_t)p.frame_id, (uint32_t)id));
+    ctx.start_iteration();
+    int px, py;
+    const float3 L = mlt_sample_path(sc, ctx, px, py, rays);
+    weights[id] = luminance(L);
+  }
+  if (rays) atomicAdd(ray_count, rays);
+}
+
+BN_DEV void film_splat(float* film, int W, int H, int px, int py, float3 c) {  // Film.Accumulate, Film.fs:48-53 (atomic here)
+  float* d = film + ((size_t)(H - py - 1) * W + px) * 3;
+  atomicAdd(d, c.x); atomicAdd(d + 1, c.y); atomicAdd(d + 2, c.z);
+}
+
+__global__ void __launch_bounds__(128) k_mlt_chains(DScene sc, MltParams p, MltState st, float* __restrict__ film, unsigned int* __restrict__ per_chain_accepted,
+                                                    unsigned long long* counters /* [0] rays [1] accepted [2] proposed */) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = p.chain_begin + tid;
+  if (chain >= p.chain_end) return;
+  unsigned long long rays = 0;
+  uint32_t sampler = xxhash32_two((uint32_t)p.frame_id, (uint32_t)chain);  // Sampler(FrameId, chainId), :285
+  // AliasTable(BootstrapWeights).Sample never takes an alias: a uniform pick (:286)
+  const float u = lcg(sampler) * (float)p.n_bootstrap;
+  const int bootstrap_id = min((int)u, p.n_bootstrap - 1);
+  MltCtx ctx{p, st, tid, {}};
+  ctx.init(xxhash32_two((uint32_t)p.frame_id, (uint32_t)bootstrap_id));
+  ctx.start_iteration();
+  int px, py;
+  float3 L = mlt_sample_path(sc, ctx, px, py, rays);
+  float y = luminance(L);
+  ctx.accept();
+  ctx.m.inner = xxhash32_three((uint32_t)chain, (uint32_t)bootstrap_id, (uint32_t)p.frame_id);  // :307
+  float3 radiance = splat(0.f);
+  unsigned int accepted = 0;
+  for (int k = 0; k < p.mutation_per_chain; ++k) {
+    ctx.start_iteration();
+    int nx, ny;
+    const float3 Ln = mlt_sample_path(sc, ctx, nx, ny, rays);
+    const float yn = luminance(Ln);
+    const float a = net_min(1.f, yn / y);
+    const float w_old = (1.f - a) / __fmaf_rn(y, p.inv_b, p.large_step_prob);
+    radiance = radiance + w_old * L;
+    const float w_new = (a + (ctx.m.large_step ? 1.f : 0.f)) / __fmaf_rn(yn, p.inv_b, p.large_step_prob);
+    if (lcg(sampler) < a) {
+      ++accepted;
+      film_splat(film, p.width, p.height, px, py, radiance * p.inv_eff);
+      radiance = w_new * Ln;
+      px = nx; py = ny; L = Ln; y = yn;
+      ctx.accept();
+    } else {
+      if (a > 0.f) film_splat(film, p.width, p.height, nx, ny, (w_new * p.inv_eff) * Ln);
+      ctx.reject();
+    }
+  }
+  film_splat(film, p.width, p.height, px, py, radiance * p.inv_eff);
+  if (per_chain_accepted) per_chain_accepted[tid] = accepted;
+  atomicAdd(counters, rays);
+  atomicAdd(counters + 1, (unsigned long long)accepted);
+  atomicAdd(counters + 2, (unsigned long long)p.mutation_per_chain);
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+namespace {
+
+bool ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  bnhost::set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return false;
+}
+#define MLT_CUDA(call)                            \
+  do {                                            \
+    if (!ok((call), #call)) return BN_ERR_CUDA;   \
+  } while (0)
+
+int validate(const BnScene* s, const BnMltParams* p) {
+  if (!s || !p || p->width <= 0 || p->height <= 0 || p->mutations_per_pixel <= 0 || p->max_depth < 0 || p->n_bootstrap <= 0 || p->n_chains <= 0 ||
+      p->chain_begin < 0 || p->chain_end > p->n_chains || p->chain_begin > p->chain_end || (p->strategy != BN_MLT_GAUSSIAN && p->strategy != BN_MLT_KELEMEN)) {
+    bnhost::set_error("bn_render_pssmlt: invalid BnMltParams");
+    return BN_ERR_INVALID;
+  }
+  if (s->poisoned) { bnhost::set_error("scene is unusable after an earlier CUDA error"); return BN_ERR_CUDA; }
+  if (s->d.n_light_inst == 0) { bnhost::set_error("LightSamplerBase: No light primitives found."); return BN_ERR_NO_LIGHT; }
+  return BN_OK;
+}
+
+struct MltBuffers {
+  float* f = nullptr;  // value | backup
+  int* i = nullptr;    // last_mod | mod_backup
+  ~MltBuffers() { if (f) cudaFree(f); if (i) cudaFree(i); }
+  int alloc(size_t n_threads, int xs_len, MltState& st) {
+    const size_t n = n_threads * (size_t)xs_len;
+    MLT_CUDA(cudaMalloc((void**)&f, 2 * n * sizeof(float)));
+    MLT_CUDA(cudaMalloc((void**)&i, 2 * n * sizeof(int)));
+    st.value = f; st.backup = f + n; st.last_mod = i; st.mod_backup = i + n;
+    return BN_OK;
+  }
+};
+
+MltParams device_params(const BnMltParams* p) {
+  MltParams d{};
+  d.width = p->width; d.height = p->height; d.max_depth = p->max_depth; d.rr_depth = p->rr_depth; d.frame_id = p->frame_id;
+  d.n_bootstrap = p->n_bootstrap; d.n_chains = p->n_chains; d.strategy = p->strategy; d.p0 = p->p0; d.p1 = p->p1;
+  d.large_step_prob = p->large_step_prob; d.chain_begin = p->chain_begin; d.chain_end = p->chain_end;
+  d.xs_len = 4 + 7 * p->max_depth;
+  return d;
+}
+
+// phase 1 on the device; weights_host receives BootstrapWeights
+int run_bootstrap(BnScene* s, const BnMltParams* p, cudaStream_t stream, std::vector<float>& weights_host, uint64_t& rays, double& ms) {
+  MltParams dp = device_params(p);
+  const int threads = std::min<long long>((long long)s->num_sms * 16 * 128, ((long long)p->n_bootstrap + 127) / 128 * 128);
+  dp.n_threads = threads;
+  MltBuffers buf;
+  MltState st{};
+  int rc = buf.alloc((size_t)threads, dp.xs_len, st);
+  if (rc != BN_OK) return rc;
+  float* d_w = nullptr;
+  unsigned long long* d_rays = nullptr;
+  MLT_CUDA(cudaMalloc((void**)&d_w, sizeof(float) * (size_t)p->n_bootstrap));
+  MLT_CUDA(cudaMalloc((void**)&d_rays, sizeof(unsigned long long)));
+  MLT_CUDA(cudaMemsetAsync(d_rays, 0, sizeof(unsigned long long), stream));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, stream);
+  k_mlt_bootstrap<<<threads / 128, 128, 0, stream>>>(s->d, dp, st, d_w, d_rays);
+  cudaEventRecord(e1, stream);
+  weights_host.resize((size_t)p->n_bootstrap);
+  cudaError_t e = cudaMemcpyAsync(weights_host.data(), d_w, sizeof(float) * (size_t)p->n_bootstrap, cudaMemcpyDeviceToHost, stream);
+  unsigned long long r = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&r, d_rays, sizeof r, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  float t = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_w); cudaFree(d_rays);
+  if (e != cudaSuccess) { s->poisoned = true; ok(e, "pssmlt bootstrap"); return BN_ERR_CUDA; }
+  rays = r; ms = t;
+  return BN_OK;
+}
+
+int render_pssmlt(BnScene* s, const BnMltParams* p, float* d_film, cudaStream_t stream, BnMltStats* stats, unsigned int* per_chain_host) {
+  int rc = validate(s, p);
+  if (rc != BN_OK) return rc;
+  MLT_CUDA(cudaSetDevice(s->device));
+  std::vector<float> w;
+  uint64_t rays_boot = 0;
+  double ms_boot = 0;
+  rc = run_bootstrap(s, p, stream, w, rays_boot, ms_boot);
+  if (rc != BN_OK) return rc;
+  float sum = 0.f;
+  for (float x : w) sum = sum + x;  // Array.average (PSSMLT.fs:394): sequential fp32 sum / n, on the host
+  const float B = sum / (float)p->n_bootstrap;
+  BnMltStats out{};
+  out.b = B; out.rays = rays_boot; out.bootstrap_ms = ms_boot;
+  const int n_run = p->chain_end - p->chain_begin;
+  if (B != 0.f && n_run > 0) {
+    MltParams dp = device_params(p);
+    dp.mutation_per_chain = (int)(((uint64_t)p->mutations_per_pixel * (uint64_t)p->width * (uint64_t)p->height + (uint64_t)p->n_chains - 1ull) / (uint64_t)p->n_chains);
+    dp.inv_eff = 1.0f / ((float)dp.mutation_per_chain * (float)p->n_chains / (float)(p->width * p->height));
+    dp.inv_b = 1.0f / B;
+    const int threads = (n_run + 127) / 128 * 128;
+    dp.n_threads = threads;
+    MltBuffers buf;
+    MltState st{};
+    rc = buf.alloc((size_t)threads, dp.xs_len, st);
+    if (rc != BN_OK) return rc;
+    unsigned long long* d_cnt = nullptr;
+    unsigned int* d_acc = nullptr;
+    MLT_CUDA(cudaMalloc((void**)&d_cnt, 3 * sizeof(unsigned long long)));
+    MLT_CUDA(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), stream));
+    if (per_chain_host) MLT_CUDA(cudaMalloc((void**)&d_acc, sizeof(unsigned int) * (size_t)threads));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, stream);
+    k_mlt_chains<<<threads / 128, 128, 0, stream>>>(s->d, dp, st, d_film, d_acc, d_cnt);
+    cudaEventRecord(e1, stream);
+    unsigned long long cnt[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && per_chain_host) e = cudaMemcpyAsync(per_chain_host, d_acc, sizeof(unsigned int) * (size_t)n_run, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    float t = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_cnt);
+    if (d_acc) cudaFree(d_acc);
+    if (e != cudaSuccess) { s->poisoned = true; ok(e, "pssmlt chains"); return BN_ERR_CUDA; }
+    out.rays += cnt[0]; out.accepted = cnt[1]; out.proposed = cnt[2]; out.chains_ms = t;
+  }
+  if (stats) *stats = out;
+  return BN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bn_pssmlt_bootstrap(BnScene* s, const BnMltParams* p, float* weights) {
+  if (!weights) { bnhost::set_error("bn_pssmlt_bootstrap: NULL argument"); return BN_ERR_INVALID; }
+  int rc = validate(s, p);
+  if (rc != BN_OK) return rc;
+  MLT_CUDA(cudaSetDevice(s->device));
+  std::vector<float> w;
+  uint64_t rays = 0;
+  double ms = 0;
+  rc = run_bootstrap(s, p, nullptr, w, rays, ms);
+  if (rc == BN_OK) std::copy(w.begin(), w.end(), weights);
+  return rc;
+}
+
+int bn_render_pssmlt_device(BnScene* s, const BnMltParams* p, void* d_film, void* stream, BnMltStats* stats) {
+  if (!d_film) { bnhost::set_error("bn_render_pssmlt_device: NULL argument"); return BN_ERR_INVALID; }
+  return render_pssmlt(s, p, static_cast<float*>(d_film), static_cast<cudaStream_t>(stream), stats, nullptr);
+}
+
+// `stats->reserved` != 0 on entry is not used; per-chain accepted counts are exposed through the debug entry below.
+int bn_render_pssmlt(BnScene* s, const BnMltParams* p, float* film, BnMltStats* stats) {
+  if (!film) { bnhost::set_error("bn_render_pssmlt: NULL argument"); return BN_ERR_INVALID; }
+  int rc = validate(s, p);
+  if (rc != BN_OK) return rc;
+  MLT_CUDA(cudaSetDevice(s->device));
+  const size_t len = (size_t)p->width * p->height * 3;
+  float* d = nullptr;
+  MLT_CUDA(cudaMalloc((void**)&d, len * sizeof(float)));
+  if (!ok(cudaMemcpy(d, film, len * sizeof(float), cudaMemcpyHostToDevice), "copy film")) { cudaFree(d); return BN_ERR_CUDA; }
+  rc = render_pssmlt(s, p, d, nullptr, stats, nullptr);
+  if (rc == BN_OK && !ok(cudaMemcpy(film, d, len * sizeof(float), cudaMemcpyDeviceToHost), "copy film")) rc = BN_ERR_CUDA;
+  cudaFree(d);
+  return rc;
+}
+
+// test hook (not in the public header): per-chain accepted mutation counts next to the film
+__attribute__((visibility("default"))) int bn_debug_render_pssmlt_chains(BnScene* s, const BnMltParams* p, float* film, BnMltStats* stats, unsigned int* per_chain_accepted) {
+  if (!film || !per_chain_accepted) return BN_ERR_INVALID;
+  int rc = validate(s, p);
+  if (rc != BN_OK) return rc;
+  MLT_CUDA(cudaSetDevice(s->device));
+  const size_t len = (size_t)p->width * p->height * 3;
+  float* d = nullptr;
+  MLT_CUDA(cudaMalloc((void**)&d, len * sizeof(float)));
+  cudaMemcpy(d, film, len * sizeof(float), cudaMemcpyHostToDevice);
+  rc = render_pssmlt(s, p, d, nullptr, stats, per_chain_accepted);
+  if (rc == BN_OK) cudaMemcpy(film, d, len * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return rc;
+}
+
+}  // extern "C"

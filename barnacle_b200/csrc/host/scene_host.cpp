@@ -509,6 +509,15 @@ BnHostScene* build_scene(const std::string& text, const std::string& base_dir, f
     scene->info.spp = in.get("spp") ? in.get("spp")->as_int() : 1;
     scene->info.max_depth = in.get("max-depth") ? in.get("max-depth")->as_int() : 8;
     scene->info.rr_depth = in.get("rr-depth") ? in.get("rr-depth")->as_int() : 5;
+    scene->info.n_bootstrap = in.get("n-bootstrap") ? in.get("n-bootstrap")->as_int() : 4 * 1024 * 1024;
+    scene->info.n_chains = in.get("n-chains") ? in.get("n-chains")->as_int() : 1024;
+    scene->info.large_step_prob = in.get("large-step-prob") ? in.get("large-step-prob")->as_f32() : 0.5f;
+    scene->info.mutation_strategy = BN_MLT_GAUSSIAN;
+    if (const bnjson::Value* ms = in.get("mutation-strategy")) {
+      if (ms->as_string() == "Gaussian") scene->info.mutation_strategy = BN_MLT_GAUSSIAN;
+      else if (ms->as_string() == "Kelemen") scene->info.mutation_strategy = BN_MLT_KELEMEN;
+      else throw std::runtime_error("Unknown mutation strategy: " + ms->as_string());
+    }
   }
   BnCamera cam{};
   {

@@ -21,7 +21,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _ffi
-from ._ffi import BarnacleError, BnHostSceneInfo, BnRenderParams, BnStats, check
+from ._ffi import BarnacleError, BnHostSceneInfo, BnMltParams, BnMltStats, BnRenderParams, BnStats, check
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("tmax", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("instance", "<i4"), ("primitive", "<i4")])
@@ -54,6 +54,19 @@ def make_params(width, height, spp, max_depth=8, rr_depth=5, frame_id=0, sample_
     x0, y0, x1, y1 = rect if rect is not None else (0, 0, width, height)
     return BnRenderParams(width, height, spp, max_depth, rr_depth, frame_id, sample_begin,
                           spp if sample_end is None else sample_end, x0, y0, x1, y1, flags, interleave[0], interleave[1], integrator)
+
+
+def make_mlt_params(width, height, mutations_per_pixel, max_depth=8, rr_depth=5, frame_id=0, n_bootstrap=4 * 1024 * 1024, n_chains=1024,
+                    strategy="Gaussian", large_step_prob=0.5, chain_begin=0, chain_end=None) -> BnMltParams:
+    """PSSMLTIntegrator's parameters with the reference's defaults (Loader.fs:189-203)."""
+    if strategy == "Gaussian":
+        st, p0, p1 = _ffi.BN_MLT_GAUSSIAN, 1e-2, 0.0
+    elif strategy == "Kelemen":
+        st, p0, p1 = _ffi.BN_MLT_KELEMEN, 1.0 / 1024.0, 1.0 / 16.0
+    else:
+        raise BarnacleError(f"Unknown mutation strategy: {strategy}")
+    return BnMltParams(width, height, mutations_per_pixel, max_depth, rr_depth, frame_id, n_bootstrap, n_chains, st, p0, p1, large_step_prob,
+                       chain_begin, n_chains if chain_end is None else chain_end)
 
 
 class Film:
@@ -132,6 +145,24 @@ class GpuScene:
         out = np.empty((ns, params.y1 - params.y0, params.x1 - params.x0, 3), dtype=np.float32)
         check(self._lib.bn_render_radiance(self._h, C.byref(params), out.ctypes.data), "bn_render_radiance")
         return out
+
+    def render_pssmlt(self, params: BnMltParams, film: np.ndarray | None = None):
+        """bn_render_pssmlt: accumulates INTO `film` (zeros if None); returns (film, BnMltStats)."""
+        if film is None:
+            film = np.zeros((params.height * params.width, 3), dtype=np.float32)
+        st = BnMltStats()
+        check(self._lib.bn_render_pssmlt(self._h, C.byref(params), film.ctypes.data, C.byref(st)), "bn_render_pssmlt")
+        return film, st
+
+    def render_pssmlt_device(self, params: BnMltParams, d_film_ptr: int, stream: int = 0) -> BnMltStats:
+        st = BnMltStats()
+        check(self._lib.bn_render_pssmlt_device(self._h, C.byref(params), C.c_void_p(d_film_ptr), C.c_void_p(stream), C.byref(st)), "bn_render_pssmlt_device")
+        return st
+
+    def pssmlt_bootstrap(self, params: BnMltParams) -> np.ndarray:
+        w = np.empty(params.n_bootstrap, dtype=np.float32)
+        check(self._lib.bn_pssmlt_bootstrap(self._h, C.byref(params), w.ctypes.data), "bn_pssmlt_bootstrap")
+        return w
 
     def trace(self, rays: np.ndarray, any_hit: bool = False) -> np.ndarray:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
@@ -215,12 +246,20 @@ class Scene:
     def Render(self, t: float, filename: str | None, device: int = 0) -> float:
         """Render.fs:10-19.  Returns the seconds spent in Integrator.Render (the
         reference's Stopwatch region)."""
-        if self.integrator_type not in GpuPathTracingIntegrator.KINDS:
-            raise BarnacleError(f"integrator '{self.integrator_type}' is outside the GPU hot path (path-tracing, direct, normal)")
         self.Film.Clear()
         gpu = self.gpu(device)
         t0 = time.perf_counter()
-        self.Integrator.Render(gpu, self.Film)
+        if self.integrator_type == "pssmlt":
+            i = self.info
+            p = make_mlt_params(i.width, i.height, i.spp, i.max_depth, i.rr_depth, 0, i.n_bootstrap, i.n_chains,
+                                "Kelemen" if i.mutation_strategy == _ffi.BN_MLT_KELEMEN else "Gaussian", i.large_step_prob)
+            _, st = gpu.render_pssmlt(p, self.Film.Pixels)
+            if st.b == 0.0:
+                print("Warning: all bootstrap samples are zero, exiting...")
+            else:
+                print(f"Accepted mutation count: {st.accepted}\nProposed mutation count: {st.proposed}\nAcceptance rate: {st.accepted / max(st.proposed, 1):f}")
+        else:
+            self.Integrator.Render(gpu, self.Film)
         dt = time.perf_counter() - t0
         print(f"Render time: {dt:f} seconds")
         if filename:

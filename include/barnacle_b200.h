@@ -247,6 +247,41 @@ BN_API int bn_film_to_rgba8_device(BnScene* scene, const void* d_film_rgb, int32
  * HOST pointer. */
 BN_API int bn_render_radiance(BnScene* scene, const BnRenderParams* params, float* radiance);
 
+/* ---- PSSMLT ("next" row N1: PSSMLTIntegrator, Extensions/Integrator/PSSMLT.fs) ------------- */
+
+enum { BN_MLT_GAUSSIAN = 0, BN_MLT_KELEMEN = 1 };  /* MutationStrategy, PSSMLT.fs:15-18 */
+
+typedef struct BnMltParams {
+  int32_t width, height;
+  int32_t mutations_per_pixel; /* PSSMLTIntegrator's `mutationPerPixel` (the JSON `spp`) */
+  int32_t max_depth, rr_depth, frame_id;
+  int32_t n_bootstrap;         /* default 4*1024*1024 (Loader.fs:190) */
+  int32_t n_chains;            /* default 1024        (Loader.fs:191) */
+  int32_t strategy;            /* BN_MLT_GAUSSIAN (sigma = p0, default 1e-2) | BN_MLT_KELEMEN (epsMin = p0, epsMax = p1; 1/1024, 1/16) */
+  float p0, p1;
+  float large_step_prob;       /* default 0.5 (Loader.fs:202) */
+  /* multi-GPU shard: only chains [chain_begin, chain_end) are run (the bootstrap is always complete) */
+  int32_t chain_begin, chain_end;
+} BnMltParams;
+
+typedef struct BnMltStats {
+  float b;                     /* PSSMLTIntegrator.B: mean bootstrap luminance (PSSMLT.fs:394) */
+  uint32_t reserved;
+  uint64_t accepted, proposed; /* AcceptedMutationCount / ProposedMutationCount of the chains run */
+  uint64_t rays;               /* closest-hit + any-hit rays traced (bootstrap + chains) */
+  double bootstrap_ms, chains_ms; /* device time of the two phases */
+} BnMltStats;
+
+/* Replaces PSSMLTIntegrator.Render (PSSMLT.fs:379-414): bootstrap, B, chains, film splats
+ * (atomic adds instead of the reference's racy Film.Accumulate).  film_rgb: HOST
+ * pointer, W*H*3 floats, Film.Pixels layout; accumulated INTO (the caller clears it, as
+ * Scene.Render does). */
+BN_API int bn_render_pssmlt(BnScene* scene, const BnMltParams* params, float* film_rgb, BnMltStats* stats);
+/* Same with the film on the device (multi-GPU reduce). */
+BN_API int bn_render_pssmlt_device(BnScene* scene, const BnMltParams* params, void* d_film_rgb, void* cuda_stream, BnMltStats* stats);
+/* Phase 1 only: BootstrapWeights[n_bootstrap] (PSSMLT.fs:247-273), HOST pointer — parity tests. */
+BN_API int bn_pssmlt_bootstrap(BnScene* scene, const BnMltParams* params, float* weights);
+
 /* ---- host-side scene builder (stands in for the managed host: JSON schema of
  *      Extensions/Scene/Loader.fs, Scene.Traverse, BVHNode.Build, AliasTable) -- */
 
@@ -257,6 +292,10 @@ typedef struct BnHostSceneInfo {
   int32_t tone_mapping;           /* 0 identity, 1 aces, 2 gamma (Base/Film.fs:10-13) */
   int32_t integrator;             /* 0 normal, 1 direct, 2 path-tracing, 3 pssmlt (Loader.fs:185-204) */
   int32_t spp, max_depth, rr_depth;
+  /* pssmlt only (Loader.fs:189-203) */
+  int32_t n_bootstrap, n_chains;
+  int32_t mutation_strategy;      /* BN_MLT_* */
+  float large_step_prob;
 } BnHostSceneInfo;
 
 /* Scene.Load (Loader.fs:277-281) + Scene.Traverse(t=time) + BVHAggregate +

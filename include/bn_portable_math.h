@@ -71,4 +71,48 @@ BN_HD float bn_atanf(float x) {
   return copysignf(y, x);
 }
 
+/* ---- log / exp (PSSMLT: ErfInv of the Gaussian mutation, Kelemen mutation; PSSMLT.fs:67-68,125-134) ----
+ * Cephes logf / expf with the exponent handled through the IEEE bit pattern, so both
+ * sides execute the same integer and fp32 operations.  Domain: positive normal x for
+ * log; |x| < 80 for exp. */
+BN_HD float bn_uint_as_float(unsigned int u) { union { unsigned int u; float f; } c; c.u = u; return c.f; }
+BN_HD unsigned int bn_float_as_uint(float f) { union { unsigned int u; float f; } c; c.f = f; return c.u; }
+
+BN_HD float bn_logf(float x) {
+  unsigned int b = bn_float_as_uint(x);
+  int e = (int)((b >> 23) & 255u) - 126;                     /* x = m * 2^e, m in [0.5, 1) */
+  float m = bn_uint_as_float((b & 0x007FFFFFu) | 0x3F000000u);
+  if (m < 0.70710678118654752440f) { e -= 1; m = (m + m) - 1.0f; } else { m = m - 1.0f; }
+  float z = m * m;
+  float y = fmaf(7.0376836292e-2f, m, -1.1514610310e-1f);
+  y = fmaf(y, m, 1.1676998740e-1f);
+  y = fmaf(y, m, -1.2420140846e-1f);
+  y = fmaf(y, m, 1.4249322787e-1f);
+  y = fmaf(y, m, -1.6668057665e-1f);
+  y = fmaf(y, m, 2.0000714765e-1f);
+  y = fmaf(y, m, -2.4999993993e-1f);
+  y = fmaf(y, m, 3.3333331174e-1f);
+  y = y * m * z;
+  float fe = (float)e;
+  y = fmaf(-2.12194440e-4f, fe, y);
+  y = fmaf(-0.5f, z, y);
+  float r = m + y;
+  return fmaf(0.693359375f, fe, r);
+}
+
+BN_HD float bn_expf(float x) {
+  float z = floorf(fmaf(1.44269504088896341f, x, 0.5f));
+  x = fmaf(z, -0.693359375f, x);
+  x = fmaf(z, 2.12194440e-4f, x);
+  int n = (int)z;
+  float xx = x * x;
+  float p = fmaf(1.9875691500e-4f, x, 1.3981999507e-3f);
+  p = fmaf(p, x, 8.3334519073e-3f);
+  p = fmaf(p, x, 4.1665795894e-2f);
+  p = fmaf(p, x, 1.6666665459e-1f);
+  p = fmaf(p, x, 5.0000001201e-1f);
+  float r = fmaf(p, xx, x) + 1.0f;
+  return r * bn_uint_as_float((unsigned int)(n + 127) << 23);   /* ldexp(r, n), -126 <= n <= 127 */
+}
+
 #endif /* BN_PORTABLE_MATH_H */

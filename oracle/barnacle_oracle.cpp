@@ -55,6 +55,8 @@ inline void o_sincos(float x, float& s, float& c) {
   else { s = sinf(x); c = cosf(x); }
 }
 inline float o_atan(float x) { return g_portable_math ? bn_atanf(x) : atanf(x); }
+inline float o_log(float x) { return g_portable_math ? bn_logf(x) : logf(x); }
+inline float o_exp(float x) { return g_portable_math ? bn_expf(x) : expf(x); }
 
 constexpr float kPi = 3.14159274101257324f;  // MathF.PI
 constexpr float kInf = std::numeric_limits<float>::infinity();
@@ -859,6 +861,160 @@ V3 integrator_li(const Scene& s, const BnRenderParams* p, const Ray& ray, Sample
   return path_li<COUNT>(s, ray, sp, p->max_depth, p->rr_depth, ps, ce, cs);
 }
 
+// =====================================================================================
+// PSSMLT — Extensions/Integrator/PSSMLT.fs ("next" row N1)
+// =====================================================================================
+struct PrimarySample {  // PSSMLT.fs:20-33
+  float value, value_backup;
+  int last_mod, mod_backup;
+};
+
+struct MltSampler {  // PSSMLT.fs:35-150
+  Sampler inner;
+  float large_step_prob;
+  int strategy;
+  float p0, p1;
+  PrimarySample* xs;
+  bool large_step = false;
+  int last_large_step_iteration = 0, current_iteration = 0, sample_index = 0, initialized = 0;
+
+  void start_iteration() {  // :57-60 (no draw at iteration 0: short-circuit ||)
+    large_step = current_iteration == 0 || inner.next1d() < large_step_prob;
+    current_iteration++;
+    sample_index = 0;
+  }
+  static float erf_inv(float x) {  // :68-96
+    x = net_min(net_max(x, -0.99999f), 0.99999f);
+    float w = -o_log(fmaf(x, -x, 1.f));
+    if (w < 5.f) {
+      w = w - 2.5f;
+      float p = 2.81022636e-08f;
+      p = fmaf(p, w, 3.43273939e-07f);
+      p = fmaf(p, w, -3.5233877e-06f);
+      p = fmaf(p, w, -4.39150654e-06f);
+      p = fmaf(p, w, 0.00021858087f);
+      p = fmaf(p, w, -0.00125372503f);
+      p = fmaf(p, w, -0.00417768164f);
+      p = fmaf(p, w, 0.246640727f);
+      return fmaf(p, w, 1.50140941f) * x;
+    }
+    w = sqrtf(w) - 3.f;
+    float p = -0.000200214257f;
+    p = fmaf(p, w, 0.000100950558f);
+    p = fmaf(p, w, 0.00134934322f);
+    p = fmaf(p, w, -0.00367342844f);
+    p = fmaf(p, w, 0.00573950773f);
+    p = fmaf(p, w, -0.0076224613f);
+    p = fmaf(p, w, 0.00943887047f);
+    p = fmaf(p, w, 1.00167406f);
+    return fmaf(p, w, 2.83297682f) * x;
+  }
+  float next1d() {  // EnsureReady(GetNextIndex()), :62-138
+    const int index = sample_index++;
+    PrimarySample& x = xs[index];
+    if (initialized <= index) { x = PrimarySample{0.f, 0.f, 0, 0}; initialized = index + 1; }
+    if (x.last_mod < last_large_step_iteration) { x.value = inner.next1d(); x.last_mod = last_large_step_iteration; }
+    x.value_backup = x.value; x.mod_backup = x.last_mod;  // BackUp
+    float v;
+    if (large_step) {
+      v = inner.next1d();
+    } else if (strategy == BN_MLT_GAUSSIAN) {
+      float normal_sample = sqrtf(2.f) * erf_inv(fmaf(2.f, inner.next1d(), -1.f));
+      float effective_sigma = p0 * sqrtf((float)(current_iteration - x.last_mod));
+      v = fmaf(normal_sample, effective_sigma, x.value);
+    } else {  // Kelemen(epsMin = p0, epsMax = p1)
+      v = x.value;
+      float a = o_log(p1 / p0);
+      for (int k = x.last_mod; k <= current_iteration - 1; ++k) {
+        float u1 = inner.next1d() - 0.5f;
+        float u2 = u1 < 0.f ? 1.f + 2.f * u1 : 2.f * u1;
+        v = v + copysignf(p1 * o_exp(-a * u2), u1);
+      }
+    }
+    x.value = v - floorf(v);
+    x.last_mod = current_iteration;
+    return x.value;
+  }
+  V2 next2d() { float a = next1d(); float b = next1d(); return {a, b}; }
+  void reject() {  // :142-146
+    for (int i = 0; i < initialized; ++i) { xs[i].value = xs[i].value_backup; xs[i].last_mod = xs[i].mod_backup; }
+    current_iteration--;
+  }
+  void accept() { if (large_step) last_large_step_iteration = current_iteration; }  // :148-150
+};
+
+// PSSMLTIntegrator.Li — PSSMLT.fs:172-245: PathTracingIntegrator.Li with a FIXED 7 dimensions per
+// bounce (drawn on every hit, used or not), fed by the MLT sampler.
+inline V3 mlt_li(const Scene& s, Ray ray, MltSampler& sampler, int max_depth, int rr_depth, PathStats& ps) {
+  V3 L{0, 0, 0}, beta{1, 1, 1};
+  int depth = 0;
+  Interaction it{};
+  float prev_bsdf_pdf = 0.f;
+  while (depth < max_depth) {
+    float t = kInf;
+    ps.extend++;
+    if (!scene_closest<false>(s, ray, it, t, nullptr)) { depth = max_depth; continue; }
+    const BnInstance& in = s.inst[it.inst];
+    if (in.light_id >= 0) {
+      LightEval le = light_sampler_eval(s, ray.o, it);
+      float w = depth == 0 ? 1.f : prev_bsdf_pdf * (1.f / (le.pdf + prev_bsdf_pdf));
+      L = vfma(beta, le.L * w, L);
+    }
+    float u_light = sampler.next1d();
+    V2 u_emit = sampler.next2d();
+    float u_lobe = sampler.next1d();
+    V2 u_bsdf = sampler.next2d();
+    float u_rr = sampler.next1d();
+    if (in.material_id < 0) { depth = max_depth; continue; }
+    const BnMaterial& mat = s.mats[in.material_id];
+    LightSample ls = light_sampler_sample(s, it.geom.p, u_light, u_emit);
+    Ray shadow{it.geom.p, ls.wi};
+    float dist = length(ls.eval.p - it.geom.p);
+    V3 wo_l = world_to_local(it.geom.onb, -ray.d);
+    if (ls.eval.pdf != 0.f) {
+      ps.shadow++;
+      if (!scene_any<false>(s, shadow, dist - 1e-3f, nullptr)) {
+        BSDFEval fe = material_eval(mat, wo_l, world_to_local(it.geom.onb, ls.wi));
+        L = vfma(beta * fe.bsdf, ls.eval.L * (1.f / (fe.pdf + ls.eval.pdf)), L);
+      }
+    }
+    BSDFSample bs = material_sample(mat, wo_l, u_lobe, u_bsdf);
+    bs.wi = local_to_world(it.geom.onb, bs.wi);
+    prev_bsdf_pdf = bs.eval.pdf;
+    if (bs.eval.pdf == 0.f) { depth = max_depth; continue; }
+    ray = {it.geom.p, bs.wi};
+    beta = beta * bs.eval.bsdf * (1.f / bs.eval.pdf);
+    if (depth >= rr_depth) {
+      float q = net_min(1.f, net_max(beta.x, net_max(beta.y, beta.z)));
+      if (u_rr < q) beta = beta * (1.f / q);
+      else depth = max_depth;
+    }
+    depth++;
+  }
+  return L;
+}
+
+inline float luminance(V3 L) { return dot(L, V3{0.2126f, 0.7152f, 0.0722f}); }
+
+// the head shared by BootstrapSingleChain (:247-273) and every mutation of RenderSingleChain
+// (:284-300, :332-349): pixel from two primary samples, primary ray from two more, Li
+inline V3 mlt_sample_path(const Scene& s, const BnMltParams& p, MltSampler& m, int& px, int& py, PathStats& ps) {
+  V2 u = m.next2d();
+  V2 up{u.x * (float)p.width, u.y * (float)p.height};
+  px = std::min(p.width - 1, (int)up.x);
+  py = std::min(p.height - 1, (int)up.y);
+  V2 ul = m.next2d();
+  Ray ray = primary_ray(s.cam, p.width, p.height, px, py, V2{up.x - (float)px, up.y - (float)py}, ul);
+  return mlt_li(s, ray, m, p.max_depth, p.rr_depth, ps) * (1.f / 1.f);
+}
+
+inline MltSampler make_mlt_sampler(const BnMltParams& p, uint32_t seed_state, PrimarySample* xs) {
+  MltSampler m;
+  m.inner = Sampler{seed_state};
+  m.large_step_prob = p.large_step_prob; m.strategy = p.strategy; m.p0 = p.p0; m.p1 = p.p1; m.xs = xs;
+  return m;
+}
+
 }  // namespace
 
 // =============================================================================
@@ -1055,6 +1211,117 @@ BO_API int bo_render(const BoScene* sc, const BnRenderParams* p, float* film, ui
   }
   if (counters_extend) export_counters(tce, counters_extend);
   if (counters_shadow) export_counters(tcs, counters_shadow);
+  return 0;
+}
+
+// PSSMLTIntegrator.Render phase 1 — PSSMLT.fs:382-392: BootstrapWeights[n_bootstrap]
+BO_API int bo_pssmlt_bootstrap(const BoScene* sc, const BnMltParams* p, float* weights, uint64_t* rays, int threads) {
+  const Scene& s = sc->s;
+  if (s.light_inst.empty()) return BN_ERR_NO_LIGHT;
+  if (threads <= 0) threads = omp_get_max_threads();
+  uint64_t total = 0;
+#pragma omp parallel num_threads(threads) reduction(+ : total)
+  {
+    std::vector<PrimarySample> xs(4 + 7 * (size_t)p->max_depth);
+#pragma omp for schedule(dynamic, 256)
+    for (int id = 0; id < p->n_bootstrap; ++id) {
+      MltSampler m = make_mlt_sampler(*p, xxhash32_two((uint32_t)p->frame_id, (uint32_t)id), xs.data());
+      m.start_iteration();
+      int px, py;
+      PathStats ps;
+      V3 L = mlt_sample_path(s, *p, m, px, py, ps);
+      weights[id] = luminance(L);
+      total += ps.extend + ps.shadow;
+    }
+  }
+  if (rays) *rays = total;
+  return 0;
+}
+
+// PSSMLTIntegrator.Render — PSSMLT.fs:379-414.  film is accumulated into (atomic adds: the
+// reference's Film.Accumulate is a racy read-modify-write).  out (may be NULL):
+// [0] B as float bits, [1] accepted, [2] proposed, [3] rays, [4] microseconds of the chain phase.
+// per_chain_accepted (may be NULL): accepted mutation count of every chain in [chain_begin, chain_end).
+BO_API int bo_render_pssmlt(const BoScene* sc, const BnMltParams* p, float* film, uint64_t* out, uint32_t* per_chain_accepted, int threads) {
+  const Scene& s = sc->s;
+  if (s.light_inst.empty()) return BN_ERR_NO_LIGHT;
+  if (threads <= 0) threads = omp_get_max_threads();
+  std::vector<float> weights((size_t)p->n_bootstrap);
+  uint64_t rays = 0;
+  bo_pssmlt_bootstrap(sc, p, weights.data(), &rays, threads);
+  float sum = 0.f;
+  for (float w : weights) sum = sum + w;          // Array.average: sequential fp32 sum / n (:394)
+  const float B = sum / (float)p->n_bootstrap;
+  uint64_t accepted = 0, proposed = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  if (B != 0.f) {
+    const int W = p->width, H = p->height;
+    const int mutation_per_chain = (int)(((uint64_t)p->mutations_per_pixel * (uint64_t)W * (uint64_t)H + (uint64_t)p->n_chains - 1ull) / (uint64_t)p->n_chains);
+    const float inv_eff = 1.f / ((float)mutation_per_chain * (float)p->n_chains / (float)(W * H));
+    const float inv_b = 1.f / B;
+    auto splat = [&](int px, int py, V3 c) {  // Film.Accumulate, Film.fs:48-53
+      float* d = film + ((size_t)(H - py - 1) * W + px) * 3;
+#pragma omp atomic
+      d[0] += c.x;
+#pragma omp atomic
+      d[1] += c.y;
+#pragma omp atomic
+      d[2] += c.z;
+    };
+#pragma omp parallel num_threads(threads) reduction(+ : accepted, proposed, rays)
+    {
+      std::vector<PrimarySample> xs(4 + 7 * (size_t)p->max_depth);
+#pragma omp for schedule(dynamic, 4)
+      for (int chain = p->chain_begin; chain < p->chain_end; ++chain) {
+        PathStats ps;
+        Sampler sampler{xxhash32_two((uint32_t)p->frame_id, (uint32_t)chain)};
+        // AliasTable(BootstrapWeights).Sample: the table never holds aliases => a uniform pick
+        float u = sampler.next1d() * (float)p->n_bootstrap;
+        const int bootstrap_id = std::min((int)u, p->n_bootstrap - 1);
+        MltSampler m = make_mlt_sampler(*p, xxhash32_two((uint32_t)p->frame_id, (uint32_t)bootstrap_id), xs.data());
+        m.start_iteration();
+        int px, py;
+        V3 L = mlt_sample_path(s, *p, m, px, py, ps);
+        float y = luminance(L);
+        m.accept();
+        m.inner = Sampler{xxhash32_three((uint32_t)chain, (uint32_t)bootstrap_id, (uint32_t)p->frame_id)};
+        V3 radiance{0, 0, 0};
+        uint32_t acc = 0;
+        for (int k = 0; k < mutation_per_chain; ++k) {
+          m.start_iteration();
+          int nx, ny;
+          V3 Ln = mlt_sample_path(s, *p, m, nx, ny, ps);
+          float yn = luminance(Ln);
+          float a = net_min(1.f, yn / y);
+          float w_old = (1.f - a) / fmaf(y, inv_b, p->large_step_prob);
+          radiance = radiance + w_old * L;
+          float w_new = (a + (m.large_step ? 1.f : 0.f)) / fmaf(yn, inv_b, p->large_step_prob);
+          if (sampler.next1d() < a) {
+            acc++;
+            splat(px, py, radiance * inv_eff);
+            radiance = w_new * Ln;
+            px = nx; py = ny; L = Ln; y = yn;
+            m.accept();
+          } else {
+            if (a > 0.f) splat(nx, ny, (w_new * inv_eff) * Ln);
+            m.reject();
+          }
+        }
+        splat(px, py, radiance * inv_eff);
+        accepted += acc;
+        proposed += (uint64_t)mutation_per_chain;
+        rays += ps.extend + ps.shadow;
+        if (per_chain_accepted) per_chain_accepted[chain - p->chain_begin] = acc;
+      }
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  if (out) {
+    uint32_t bb;
+    std::memcpy(&bb, &B, 4);
+    out[0] = bb; out[1] = accepted; out[2] = proposed; out[3] = rays;
+    out[4] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+  }
   return 0;
 }
 

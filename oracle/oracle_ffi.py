@@ -52,6 +52,8 @@ def load() -> C.CDLL:
         lib.bo_render_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_set_portable_math.argtypes = [C.c_int]
+        lib.bo_pssmlt_bootstrap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.bo_render_pssmlt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = lib
     return _lib
 
@@ -102,6 +104,23 @@ class OracleScene:
         rc = self._lib.bo_render_radiance(self._h, C.byref(params), out.ctypes.data, threads)
         assert rc == 0, rc
         return out
+
+    def pssmlt_bootstrap(self, params, threads: int = 0) -> np.ndarray:
+        w = np.empty(params.n_bootstrap, dtype=np.float32)
+        rc = self._lib.bo_pssmlt_bootstrap(self._h, C.byref(params), w.ctypes.data, None, threads)
+        assert rc == 0, rc
+        return w
+
+    def render_pssmlt(self, params, threads: int = 0):
+        """Returns (film [H*W,3], stats dict, accepted-per-chain)."""
+        film = np.zeros((params.height * params.width, 3), dtype=np.float32)
+        out = np.zeros(5, dtype=np.uint64)
+        per_chain = np.zeros(max(params.chain_end - params.chain_begin, 1), dtype=np.uint32)
+        rc = self._lib.bo_render_pssmlt(self._h, C.byref(params), film.ctypes.data, out.ctypes.data, per_chain.ctypes.data, threads)
+        assert rc == 0, rc
+        b = np.array([int(out[0])], dtype=np.uint32).view(np.float32)[0]
+        return film, {"B": float(b), "B_bits": int(out[0]), "accepted": int(out[1]), "proposed": int(out[2]), "rays": int(out[3]),
+                      "chain_seconds": int(out[4]) * 1e-6}, per_chain
 
     def render(self, params, threads: int = 0, counters: bool = False):
         """Returns (film [H*W,3], stats dict)."""

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 name = sys.argv[1] if len(sys.argv) > 1 else "cbox_bunny"
 scene = Scene.Load(os.path.join(ROOT, "scenes", name + ".json"), base_dir=ROOT)
 g = scene.gpu()
-W, H, SPP = (1024, 1024, 4)
+W, H, SPP = (int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (1024, 1024, 4)
 raw = ctypes.CDLL(_ffi.LIB_PATH)
 out = (ctypes.c_ulonglong * 20)()
 g.render(make_params(W, H, SPP))
