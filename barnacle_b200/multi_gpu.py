@@ -62,6 +62,26 @@ def owned_pixels(width: int, height: int, shard: Shard) -> int:
     return sum(width * (min((r + 1) * TILE, height) - r * TILE) for r in rows)
 
 
+def partition_chains(n_chains: int, world: int, rank: int) -> tuple[int, int]:
+    """PSSMLT: chains are independent given the (replicated) bootstrap; rank g runs a contiguous range."""
+    return (rank * n_chains) // world, ((rank + 1) * n_chains) // world
+
+
+def render_pssmlt_sharded(gpu_scene, base, film, dist=None, stream: int = 0):
+    """PSSMLT across GPUs: every rank runs the whole bootstrap (same B everywhere), its share of the
+    chains, splats into its own film (must be zeroed by the caller), one sum-reduce to rank 0."""
+    from ._ffi import BnMltParams
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    b, e = partition_chains(base.n_chains, world, rank)
+    p = BnMltParams(base.width, base.height, base.mutations_per_pixel, base.max_depth, base.rr_depth, base.frame_id, base.n_bootstrap,
+                    base.n_chains, base.strategy, base.p0, base.p1, base.large_step_prob, b, e)
+    stats = gpu_scene.render_pssmlt_device(p, film.data_ptr(), stream)
+    if world > 1:
+        dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+    return stats
+
+
 def render_sharded(gpu_scene, base: BnRenderParams, film, dist=None, stream: int = 0, mode: str = "auto"):
     """Render this rank's shard into `film` (a torch CUDA float32 tensor of W*H*3 on
     the scene's device; pixels outside the shard are written as 0) and sum-reduce to

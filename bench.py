@@ -43,6 +43,8 @@ WORKLOADS = {
     "C2": ("cbox_bunny.json", 1024, 1024, 256, "C2 cbox+stanford-bunny 1024x1024x256spp"),
     "C3": ("material_sweep.json", 1920, 1080, 1024, "C3 GGX+dielectric sweep 1920x1080x1024spp"),
     "C4": ("bunny_instanced.json", 3840, 2160, 512, "C4 4096 bunny instances 3840x2160x512spp"),
+    # "next" row N1: PSSMLT, 10 mutations per pixel = 10.5 M mutations; chains split over the GPUs
+    "C5": ("cbox_mlt.json", 1024, 1024, 10, "C5 PSSMLT cbox+bunny 1024x1024, 10.5M mutations, 65536 chains"),
 }
 MAX_DEPTH, RR_DEPTH = 8, 5
 # algorithmic bytes per traced ray in the REFERENCE layout
@@ -144,6 +146,102 @@ def run_reference(args, scene_file, W, H, SPP, label):
     }))
 
 
+def run_pssmlt(args, scene_file, W, H, SPP, label):
+    """C5: one step = one PSSMLTIntegrator.Render (bootstrap + all chains + film reduce)."""
+    import torch
+    import torch.distributed as dist
+    from barnacle_b200.multi_gpu import render_pssmlt_sharded
+    from barnacle_b200.scene import Scene, make_mlt_params
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle.oracle_ffi import OracleScene, num_threads, set_portable_math
+        scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
+        i = scene.info
+        set_portable_math(False)
+        o = OracleScene(scene.desc)
+        p = make_mlt_params(W, H, 1, i.max_depth, i.rr_depth, 0, 262144, 1024)   # bounded sample: 1 mutation/pixel, 256 Ki bootstrap
+        rays = secs = muts = 0
+        for k in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            _, st, _ = o.render_pssmlt(p)
+            if k >= args.warmup:
+                secs += time.perf_counter() - t0; rays += st["rays"]; muts += st["proposed"]
+        set_portable_math(True)
+        val = rays / secs / 1e6
+        print(json.dumps({"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": label}, "mutations_per_s": muts / secs,
+                          "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": num_threads(), "kind": "port",
+                                           "sample": "1 of 10 mutations per pixel, 262144 bootstrap paths, 1024 chains per step"},
+                          "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
+    i = scene.info
+    gpu = scene.gpu(local)
+    film = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
+    base = make_mlt_params(W, H, SPP, i.max_depth, i.rr_depth, 0, i.n_bootstrap, i.n_chains, "Gaussian", i.large_step_prob)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        film.zero_()
+        return render_pssmlt_sharded(gpu, base, film, dist if world > 1 else None, stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = muts = acc = 0
+    ms = 0.0
+    barrier()
+    for _ in range(args.steps):
+        ev0.record(); st = step(); ev1.record(); torch.cuda.synchronize()
+        ms += ev0.elapsed_time(ev1); rays += st.rays; muts += st.proposed; acc += st.accepted
+    barrier()
+    t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None   # the sampler covers the timed region only
+    host_film = torch.empty(W * H * 3, dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        if rank == 0:
+            host_film.copy_(film)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    agg = torch.tensor([ms, float(rays), float(muts), float(acc), e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        agg[0], agg[4] = mx[0], mx[4]
+    if rank == 0:
+        ms, rays, muts, acc, e2e_s = (float(x) for x in agg)
+        print(json.dumps({
+            "metric": "Mrays/s", "value": rays / ms / 1e3, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "n_chains": i.n_chains, "n_bootstrap": i.n_bootstrap, "parallelism": f"chain-split x{world} + film reduce" if world > 1 else "single GPU",
+                       "l2_flush": "film (12.6 MB) rewritten each step; working set (primary samples + scene) is L2-resident by design"},
+            "mutations_per_s": muts / (ms * 1e-3), "acceptance_rate": acc / max(muts, 1.0), "gpu_launches": 2 * args.steps * world,
+            "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12, "ms_per_step": e2e_s / args.steps * 1e3},
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "k_mlt_chains (one Markov chain per thread)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "first implementation of the next row: per-thread megakernel on the exact traversal; not yet profiled against a roofline"},
+            "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +257,8 @@ def main():
     if args.spp:
         SPP = args.spp
         label += f" [spp overridden to {SPP}]"
+    if args.workload == "C5":
+        return run_pssmlt(args, scene_file, W, H, SPP, label)
     if args.impl == "reference":
         return run_reference(args, scene_file, W, H, SPP, label)
 
@@ -216,6 +316,7 @@ def main():
             tot["render_ms"] += st.gpu_ms
     barrier()
     t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None   # the sampler covers the timed region only
     # flush.zero_() is inside ev0..ev1; subtract nothing — it is ~0.1 ms of a multi-hundred-ms step and is reported in config
     my_ms = float(sum(step_ms))
     agg = torch.tensor([my_ms, tot["extend"], tot["shadow"], tot["paths"], tot["launches"]], dtype=torch.float64, device="cuda")
@@ -277,7 +378,6 @@ def main():
     e2e_value = float(e2e_t[1]) / e2e_s / 1e6
 
     if rank == 0:
-        clk = clocks.stop(t_wall0, t_wall1)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"

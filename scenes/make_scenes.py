@@ -182,7 +182,9 @@ def main():
     dump("material_sweep.json", make_c3())
     dump("bunny_instanced.json", make_c4())
     c5 = make_c2()
-    c5["integrator"] = {"type": "pssmlt", "spp": 16, "max-depth": 8}
+    # 10 mutations per pixel at 1024x1024 = 10.5 M mutations (BASELINE C5: "10M mutations per GPU");
+    # 65 536 chains of 160 mutations: the chain count is the GPU's parallelism (reference default: 1024)
+    c5["integrator"] = {"type": "pssmlt", "spp": 10, "max-depth": 8, "n-chains": 65536}
     dump("cbox_mlt.json", c5)
     # small variants used by the parity tests (same geometry, tiny films)
     t = make_c4(n=8, width=128, height=72, spp=4)
