@@ -207,7 +207,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
   int cur_inst = -1;
   int index = 0;          // queue slot of this ray
   uint32_t tri_k = 0;     // next triangle of the held BLAS leaf
-  uint32_t tl_pos = 0;    // next entry of the flat TLAS order
+  uint32_t tl_pos = 0;    // small TLAS: bit mask of the candidate instances still to visit (visiting order)
   bool in_obj = false;
   wo = wd = winv = o = d = inv = splat(0.f);
 
@@ -278,7 +278,19 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
         if (!(scene_fast && slab_fast_ok(wo, winv))) {
           io.defer(index);
         } else if (flat) {
-          cur = kScan;
+          // Small TLAS: ONE uniform pass over the octant-ordered instance boxes with the initial t
+          // gives the candidate set (bit k = k-th instance in visiting order).  t only shrinks, so
+          // an instance that fails now fails later too; candidates are re-checked against the
+          // then-current t when their turn comes (phase S), which is the reference's test.
+          const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns & 7u) * n_inst);
+          uint32_t mask = 0u;
+          for (uint32_t k = 0; k < n_inst; ++k) {
+            const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
+            if (slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) mask |= 1u << k;
+          }
+          tl_pos = mask;
+          if (mask) cur = kScan;
+          else finish();
         } else {
           // BVHAggregate pops node 0 and tests its bounds first (BVH.fs:45-47)
           const Slab s = slab<true>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv);
@@ -395,10 +407,11 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
       if (isS) {
         const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns & 7u) * n_inst);
         bool found = false;
-        while (tl_pos < n_inst) {
-          const float4 a = __ldg(fp + 2u * tl_pos), b = __ldg(fp + 2u * tl_pos + 1u);
-          ++tl_pos;
-          if (slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) {
+        while (tl_pos != 0u) {
+          const uint32_t k = (uint32_t)__ffs((int)tl_pos) - 1u;
+          tl_pos &= tl_pos - 1u;
+          const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
+          if (ANY || slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) {
             cur = kLeafBit | kTlasBit | fbits(a.w);
             found = true;
             break;
