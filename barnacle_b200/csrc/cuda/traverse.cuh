@@ -44,7 +44,7 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;  // lane idle (a leaf ref that no scene 
 constexpr uint32_t kScan = 0xFFFFFFFEu;  // lane is at the small-TLAS ordered scan (ditto)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef BN_REFILL_MIN
-#define BN_REFILL_MIN 8
+#define BN_REFILL_MIN 12
 #endif
 constexpr int kRefillMin = BN_REFILL_MIN;  // refill when at least this many lanes are idle
 
