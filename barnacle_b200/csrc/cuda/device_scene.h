@@ -80,7 +80,7 @@ static_assert(sizeof(GInstHead) == 48, "GInstHead must be 48 B");
 // of the ray direction), each with its world AABB: 32 B per entry.
 struct __align__(16) GFlatInst {
   float bmin[3]; uint32_t slot;
-  float bmax[3]; uint32_t pad;
+  float bmax[3]; uint32_t direct_root;  // identity mesh instance: its BLAS root ref (the scan enters it without phase E); else 0xFFFFFFFF
 };
 constexpr uint32_t kFlatTlasMax = 16;  // use the ordered scan when the scene has at most this many instances
 

@@ -422,6 +422,20 @@ struct TraceIO {
     hits[i] = out;
   }
 };
+// ---- L2 read-bandwidth probe (the traversal's scene data is L2-resident, so the L2
+// rate is the second roofline denominator).  Every thread sweeps a buffer that fits L2 with
+// 16-B ld.global.cg loads (L1 bypassed), `iters` times; returns bytes read / device time.
+__global__ void __launch_bounds__(256) k_l2_sweep(const uint4* __restrict__ buf, size_t n_vec, int iters, unsigned* sink) {
+  unsigned acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; ++it)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      const uint4 v = __ldcg(buf + i);
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0xDEADBEEFu) *sink = acc;  // keeps the loads alive
+}
+
 }  // namespace bn
 
 // =================================================================================
@@ -705,11 +719,40 @@ extern "C" {
 #ifdef BN_TRAV_STATS
 // debug builds only: [closest: cntN cntT cntE cntAll sumN sumT sumE sumAll | any: same]
 __attribute__((visibility("default"))) int bn_debug_trav_stats(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, bn::g_trav_stats, sizeof(unsigned long long) * 20);
-  if (reset) { unsigned long long z[20] = {0}; cudaMemcpyToSymbol(bn::g_trav_stats, z, sizeof z); }
+  cudaMemcpyFromSymbol(out, bn::g_trav_stats, sizeof(unsigned long long) * 24);
+  if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(bn::g_trav_stats, z, sizeof z); }
   return 0;
 }
 #endif
+
+int bn_measure_l2_read_gbs(int device, uint64_t bytes, int iters, double* gbs) {
+  if (!gbs || bytes < 4096 || iters < 1) { bnhost::set_error("bn_measure_l2_read_gbs: bad argument"); return BN_ERR_INVALID; }
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); bnhost::set_error("no CUDA device"); return BN_ERR_NO_DEVICE; }
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  uint4* buf = nullptr;
+  unsigned* sink = nullptr;
+  if (cudaMalloc((void**)&buf, bytes) != cudaSuccess || cudaMalloc((void**)&sink, 4) != cudaSuccess) { cudaGetLastError(); bnhost::set_error("cudaMalloc failed"); return BN_ERR_CUDA; }
+  cudaMemset(buf, 1, bytes);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const size_t n_vec = bytes / 16;
+  const int grid = prop.multiProcessorCount * 8;
+  bn::k_l2_sweep<<<grid, 256>>>(buf, n_vec, 2, sink);  // warm the L2
+  cudaEventRecord(e0);
+  bn::k_l2_sweep<<<grid, 256>>>(buf, n_vec, iters, sink);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf); cudaFree(sink);
+  if (e != cudaSuccess || ms <= 0.f) { bnhost::set_error("L2 probe failed"); return BN_ERR_CUDA; }
+  *gbs = (double)n_vec * 16.0 * iters / (ms * 1e-3) / 1e9;
+  return BN_OK;
+}
 
 int bn_device_count(void) {
   int n = 0;

@@ -276,7 +276,7 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
         const BnInstance& in = d.instances[order[k]];
         std::memcpy(f.bmin, in.bounds_min, 12); std::memcpy(f.bmax, in.bounds_max, 12);
         f.slot = order[k];
-        f.pad = 0;
+        f.direct_root = out.inst_trav[order[k]].identity ? out.inst_trav[order[k]].root : 0xFFFFFFFFu;
       }
     }
   }

@@ -47,11 +47,15 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #define BN_REFILL_MIN 12
 #endif
 constexpr int kRefillMin = BN_REFILL_MIN;  // refill when at least this many lanes are idle
+#ifndef BN_STAY_MIN
+#define BN_STAY_MIN 12
+#endif
+constexpr int kStayMin = BN_STAY_MIN;      // phase N repeats without a vote while at least this many lanes are at a node (33: never)
 
 #ifdef BN_TRAV_STATS
 // debug builds only (python -m barnacle_b200.build --stats): phase executions and ready lanes
-__device__ unsigned long long g_trav_stats[20];
-#define BN_STAT(slot, lanes) do { if ((threadIdx.x & 31) == 0) { st_cnt[slot] += 1; st_sum[slot] += (lanes); } } while (0)
+__device__ unsigned long long g_trav_stats[24];
+#define BN_STAT(slot, lanes) do { const int n_ready_ = (lanes); if ((threadIdx.x & 31) == 0) { st_cnt[slot] += 1; st_sum[slot] += n_ready_; } } while (0)
 #else
 #define BN_STAT(slot, lanes) do { } while (0)
 #endif
@@ -305,25 +309,31 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
 
     if (nN >= nT && nN >= nE && nN >= nS) {
       // ---- phase N: one node step (64-B GNode, two slab tests)
-      BN_STAT(0, nN);
-      if (isN) {
-        const float4* np = node_base + (size_t)(cur & kIndexMask) * 4u;
-        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-        const Slab sl = slab<true>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
-        const Slab sr = slab<true>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
-        const bool pl = slab_pass<true>(sl, t), pr = slab_pass<true>(sr, t);
-        const uint32_t level = cur & kTlasBit;
-        const bool lf = ((signs >> fbits(n3.z)) & 1u) != 0u;  // left first iff dir[splitAxis] > 0 (BVH.fs:51-56 / Mesh.fs:235-240)
-        const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
-        if (pl & pr) {
-          cur = lf ? left : right;
-          stk[sp] = make_uint2(lf ? right : left, __float_as_uint(lf ? sr.tmin : sl.tmin));
-          ++sp;
-        } else if (pl | pr) {
-          cur = pl ? left : right;
-        } else {
-          pop();
+      // keep stepping while enough lanes still have a node step to do (one ballot instead of a vote)
+      bool goN = isN;
+      for (;;) {
+        BN_STAT(0, __popc(__ballot_sync(kFull, goN)));
+        if (goN) {
+          const float4* np = node_base + (size_t)(cur & kIndexMask) * 4u;
+          const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+          const Slab sl = slab<true>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
+          const Slab sr = slab<true>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
+          const bool pl = slab_pass<true>(sl, t), pr = slab_pass<true>(sr, t);
+          const uint32_t level = cur & kTlasBit;
+          const bool lf = ((signs >> fbits(n3.z)) & 1u) != 0u;  // left first iff dir[splitAxis] > 0 (BVH.fs:51-56 / Mesh.fs:235-240)
+          const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
+          if (pl & pr) {
+            cur = lf ? left : right;
+            stk[sp] = make_uint2(lf ? right : left, __float_as_uint(lf ? sr.tmin : sl.tmin));
+            ++sp;
+          } else if (pl | pr) {
+            cur = pl ? left : right;
+          } else {
+            pop();
+          }
+          goN = !(cur & kLeafBit);
         }
+        if (__popc(__ballot_sync(kFull, goN)) < kStayMin) break;
       }
     } else if (nT >= nE && nT >= nS) {
       // ---- phase T: next triangle of the held BLAS leaf (slot order), behind its own
@@ -412,7 +422,17 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
           tl_pos &= tl_pos - 1u;
           const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
           if (ANY || slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) {
-            cur = kLeafBit | kTlasBit | fbits(a.w);
+            if (fbits(b.w) != kNone) {
+              // identity mesh instance: what phase E would do (object space == world space, the BLAS
+              // root box is this box), done here so that the ray goes straight to its N / T phase
+              o = wo; d = wd; inv = winv; signs = wsigns;
+              in_obj = true;
+              cur_inst = (int)fbits(a.w);
+              tri_k = 0;
+              cur = fbits(b.w);
+            } else {
+              cur = kLeafBit | kTlasBit | fbits(a.w);
+            }
             found = true;
             break;
           }

@@ -407,6 +407,12 @@ def main():
                     "rank0_class_ms_per_step": {k: tot[k + "_ms"] / args.steps for k in ("extend", "shade", "shadow", "other")},
                     "note": "bytes/ray = 32*N_node + 48*N_tri + (24*N_inst_visited + 64*N_inst_boxpass + 64*N_inst_committed) + 48 I/O in the REFERENCE layout (SURVEY 8d), counted by the instrumented oracle "
                             f"on {cw}x{ch}x2spp of this scene; scene data is L2-resident, so this is an algorithmic-traffic rate against the HBM copy peak"}
+        # second denominator: the scene data is L2-resident, so also state the rate against
+        # the L2 read bandwidth measured here, now (32 MiB buffer, 16-B loads bypassing L1)
+        l2 = ctypes.c_double(0.0)
+        if _ffi.load().bn_measure_l2_read_gbs(local, 32 << 20, 20, ctypes.byref(l2)) == 0 and l2.value > 0 and achieved:
+            roofline["l2"] = {"peak": l2.value, "unit": "GB/s", "frac": achieved / l2.value,
+                              "peak_source": "bn_measure_l2_read_gbs: 20 sweeps of a 32 MiB L2-resident buffer, ld.global.cg.v4, CUDA events, this run"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             # ~10-30 s of CPU work: 4 spp of the workload's film (libm math, as the reference)

@@ -206,6 +206,10 @@ typedef struct BnScene BnScene;
 /* Number of usable CUDA devices (0 if none; never throws). */
 BN_API int bn_device_count(void);
 
+/* Measurement aid (bench.py roofline): read bandwidth of an L2-resident buffer of `bytes`
+ * (16-B loads that bypass L1, `iters` sweeps), in GB/s. */
+BN_API int bn_measure_l2_read_gbs(int device, uint64_t bytes, int iters, double* gbs);
+
 /* Thread-local description of the last error on this thread. */
 BN_API const char* bn_last_error(void);
 

@@ -10,7 +10,7 @@ scene = Scene.Load(os.path.join(ROOT, "scenes", name + ".json"), base_dir=ROOT)
 g = scene.gpu()
 W, H, SPP = (int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (1024, 1024, 4)
 raw = ctypes.CDLL(_ffi.LIB_PATH)
-out = (ctypes.c_ulonglong * 20)()
+out = (ctypes.c_ulonglong * 24)()
 g.render(make_params(W, H, SPP))
 raw.bn_debug_trav_stats(out, 1)
 _, st = g.render(make_params(W, H, SPP, flags=_ffi.BN_RENDER_PROFILE))
