@@ -251,6 +251,16 @@ BN_API int bn_film_to_rgba8_device(BnScene* scene, const void* d_film_rgb, int32
  * HOST pointer. */
 BN_API int bn_render_radiance(BnScene* scene, const BnRenderParams* params, float* radiance);
 
+/* ---- BVH build on the device ("next" row N2: BVHNode.Build, Util/BVH.fs:109-247) ----------
+ * Same contract as bn_host_bvh_build below (n boxes of 6 floats; nodes in the reference's
+ * preorder layout; perm[i] = original index now at slot i; returns the node count, < 0 on
+ * error) and the same bytes: node array and permutation are identical to the host builder's.
+ * Boxes must be finite.  `ms` (may be NULL) receives the device time of the build. */
+BN_API int bn_bvh_build(int device, const float* boxes, uint32_t n, BnBVHNode* nodes, uint32_t max_nodes, uint32_t* perm, float* ms);
+/* Device-pointer variant (d_nodes must hold 2n-1 nodes at most; pass max_nodes accordingly). */
+BN_API int bn_bvh_build_device(int device, const void* d_boxes, uint32_t n, void* d_nodes, uint32_t max_nodes, void* d_perm,
+                               void* cuda_stream, float* ms);
+
 /* ---- PSSMLT ("next" row N1: PSSMLTIntegrator, Extensions/Integrator/PSSMLT.fs) ------------- */
 
 enum { BN_MLT_GAUSSIAN = 0, BN_MLT_KELEMEN = 1 };  /* MutationStrategy, PSSMLT.fs:15-18 */
