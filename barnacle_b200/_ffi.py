@@ -135,6 +135,7 @@ SYMBOLS = {
     "bn_bvh_build": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_uint32, C.POINTER(BnBVHNode), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]),
     "bn_bvh_build_device": (C.c_int, [C.c_int, _VP, C.c_uint32, _VP, C.c_uint32, _VP, _VP, C.POINTER(C.c_float)]),
     "bn_host_scene_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(_VP)]),
+    "bn_host_scene_load_ex": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.c_int, C.POINTER(_VP)]),
     "bn_host_scene_load_string": (C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(_VP)]),
     "bn_host_scene_desc": (C.POINTER(BnSceneDesc), [_VP]),
     "bn_host_scene_info": (None, [_VP, C.POINTER(BnHostSceneInfo)]),

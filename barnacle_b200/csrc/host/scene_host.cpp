@@ -134,7 +134,19 @@ int build_rec(std::vector<BuildItem>& items, int first, int last, int depth, std
 }
 
 // Returns nodes; perm[i] = original index of the item now at slot i.
+thread_local int g_build_device = -1;  // >= 0: BVHs are built by bn_bvh_build on that CUDA device (bn_host_scene_load_ex)
+
 std::vector<BnBVHNode> bvh_build(const std::vector<AABB>& boxes, std::vector<uint32_t>& perm) {
+  if (g_build_device >= 0 && !boxes.empty()) {
+    static_assert(sizeof(AABB) == 24, "AABB is 6 packed floats");
+    std::vector<BnBVHNode> out(2 * boxes.size());
+    perm.resize(boxes.size());
+    const int cnt = bn_bvh_build(g_build_device, reinterpret_cast<const float*>(boxes.data()), (uint32_t)boxes.size(), out.data(), (uint32_t)out.size(),
+                                 perm.data(), nullptr);
+    if (cnt < 0) throw std::runtime_error(std::string("device BVH build failed: ") + bn_last_error());
+    out.resize((size_t)cnt);
+    return out;
+  }
   std::vector<BuildItem> items(boxes.size());
   for (size_t i = 0; i < boxes.size(); ++i) items[i] = {boxes[i], (uint32_t)i};
   std::vector<BnBVHNode> nodes;
@@ -636,6 +648,12 @@ int bn_host_scene_load(const char* json_path, const char* base_dir, float time, 
   std::stringstream ss;
   ss << in.rdbuf();
   return guarded_load(ss.str(), base_dir, time, out);
+}
+
+int bn_host_scene_load_ex(const char* json_path, const char* base_dir, float time, int build_device, BnHostScene** out) {
+  struct Restore { int prev; ~Restore() { g_build_device = prev; } } restore{g_build_device};
+  g_build_device = build_device;
+  return bn_host_scene_load(json_path, base_dir, time, out);
 }
 
 const BnSceneDesc* bn_host_scene_desc(const BnHostScene* s) { return s ? &s->desc : nullptr; }

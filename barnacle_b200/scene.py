@@ -211,11 +211,16 @@ class Scene:
         self._gpu: GpuScene | None = None
 
     @staticmethod
-    def Load(filename: str, base_dir: str | None = None, time_: float = 0.0) -> "Scene":
+    def Load(filename: str, base_dir: str | None = None, time_: float = 0.0, build_device: int | None = None) -> "Scene":
+        """build_device: CUDA ordinal whose BVH builder (bn_bvh_build) builds every BLAS and the TLAS; None = host builder.
+        The flattened scene is identical either way."""
         lib = _ffi.load()
         h = C.c_void_p()
         bd = (base_dir or os.getcwd()).encode()
-        check(lib.bn_host_scene_load(filename.encode(), bd, C.c_float(time_), C.byref(h)), "Scene.Load")
+        if build_device is None:
+            check(lib.bn_host_scene_load(filename.encode(), bd, C.c_float(time_), C.byref(h)), "Scene.Load")
+        else:
+            check(lib.bn_host_scene_load_ex(filename.encode(), bd, C.c_float(time_), int(build_device), C.byref(h)), "Scene.Load")
         return Scene(h, lib)
 
     @staticmethod

@@ -317,6 +317,10 @@ typedef struct BnHostSceneInfo {
  * relative mesh `uri`s (NULL = process CWD, like the reference). */
 BN_API int bn_host_scene_load(const char* json_path, const char* base_dir, float time, BnHostScene** out);
 BN_API int bn_host_scene_load_string(const char* json_text, const char* base_dir, float time, BnHostScene** out);
+/* Same as bn_host_scene_load, with every BVHNode.Build (each mesh's BLAS, Mesh.fs:169-171, and the
+ * TLAS, Aggregate/BVH.fs:9) done by bn_bvh_build on CUDA device `build_device` (-1: on the host).
+ * The resulting BnSceneDesc is identical either way. */
+BN_API int bn_host_scene_load_ex(const char* json_path, const char* base_dir, float time, int build_device, BnHostScene** out);
 BN_API const BnSceneDesc* bn_host_scene_desc(const BnHostScene* scene);
 BN_API void bn_host_scene_info(const BnHostScene* scene, BnHostSceneInfo* info);
 /* original (pre-BVH-permutation) index of TLAS-order instance i / BLAS-order triangle i of mesh m */

@@ -119,3 +119,21 @@ def test_rejects_non_finite_boxes(lib):
 def test_large_build(lib):
     n_nodes, ms = check_same(lib, random_boxes(1 << 20, seed=99, extent=1000.0, size=1.0))
     print(f"1 Mi boxes -> {n_nodes} nodes in {ms:.1f} ms on the device")
+
+
+def test_scene_loaded_with_device_builder_is_identical(lib, root):
+    """Scene.Load with every BVHNode.Build on the device: the flattened BnSceneDesc (TLAS, BLAS, permuted
+    triangles and instances, alias tables) equals the host-built one byte for byte."""
+    from barnacle_b200.scene import Scene
+    for name in ("cbox_bunny", "bunny_instanced_small", "bunny_instanced"):
+        path = os.path.join(root, "scenes", name + ".json")
+        a = Scene.Load(path, base_dir=root)
+        b = Scene.Load(path, base_dir=root, build_device=0)
+        da, db = a.desc.contents, b.desc.contents
+        for cnt, ptr, size in (("tlas_node_count", "tlas_nodes", 32), ("blas_node_count", "blas_nodes", 32), ("instance_count", "instances", 168),
+                               ("triangle_count", "triangles", 12), ("alias_count", "alias", 12), ("vertex_count", "vertices", 12)):
+            na, nb = getattr(da, cnt), getattr(db, cnt)
+            assert na == nb, (name, cnt)
+            assert C.string_at(getattr(da, ptr), na * size) == C.string_at(getattr(db, ptr), nb * size), (name, ptr)
+        assert np.array_equal(a.instance_permutation(), b.instance_permutation())
+        a.close(); b.close()
