@@ -458,6 +458,13 @@ struct WaveBuffers {
   float4* shq = nullptr;
   float4* rad = nullptr;
   int* defer_list = nullptr;
+  // the small per-render buffers travel with the bundle so that creating / destroying a scene
+  // (the e2e path does both per frame) allocates nothing once a device is warm
+  int* counters = nullptr;
+  size_t counters_len = 0;
+  unsigned long long* shadow_ref = nullptr;
+  float* film = nullptr;
+  size_t film_len = 0;
 };
 std::mutex g_pool_mutex;
 std::vector<WaveBuffers> g_pool;
@@ -472,16 +479,29 @@ bool cuda_ok(cudaError_t e, const char* what) {
     if (!cuda_ok((call), #call)) return BN_ERR_CUDA;   \
   } while (0)
 
-template <class T>
-int upload(BnScene* s, const std::vector<T>& v, const T** out) {
-  void* p = nullptr;
-  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-  BN_CUDA(cudaMalloc(&p, bytes));
-  s->allocs.push_back(p);
-  if (!v.empty()) BN_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-  *out = reinterpret_cast<const T*>(p);
-  return BN_OK;
-}
+// Lays the scene arrays out in one staging buffer (256-B aligned slices) so that bn_scene_create
+// costs one cudaMalloc and one cudaMemcpy whatever the number of arrays.
+struct SceneArena {
+  std::vector<unsigned char> staging;
+  struct Fix { const void** out; size_t offset; };
+  std::vector<Fix> fixes;
+  template <class T>
+  void add(const std::vector<T>& v, const T** out) {
+    const size_t off = (staging.size() + 255) & ~(size_t)255;
+    const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    staging.resize(off + bytes);
+    if (!v.empty()) std::memcpy(staging.data() + off, v.data(), v.size() * sizeof(T));
+    fixes.push_back({reinterpret_cast<const void**>(out), off});
+  }
+  int commit(BnScene* s) {
+    void* p = nullptr;
+    BN_CUDA(cudaMalloc(&p, staging.size()));
+    s->allocs.push_back(p);
+    BN_CUDA(cudaMemcpy(p, staging.data(), staging.size(), cudaMemcpyHostToDevice));
+    for (const Fix& f : fixes) *f.out = static_cast<const unsigned char*>(p) + f.offset;
+    return BN_OK;
+  }
+};
 
 size_t wave_capacity_paths() {
   const char* e = std::getenv("BN_WAVE_PATHS");
@@ -493,18 +513,20 @@ size_t wave_capacity_paths() {
 }
 
 void free_wave_buffers(WaveBuffers& w) {
-  for (void* p : {(void*)w.state[0], (void*)w.state[1], (void*)w.hits, (void*)w.shq, (void*)w.rad, (void*)w.defer_list})
+  for (void* p : {(void*)w.state[0], (void*)w.state[1], (void*)w.hits, (void*)w.shq, (void*)w.rad, (void*)w.defer_list, (void*)w.counters, (void*)w.shadow_ref, (void*)w.film})
     if (p) cudaFree(p);
   w = WaveBuffers();
 }
 
 void release_wave_buffers(BnScene* s) {  // park the scene's buffers for the next scene on this device
-  if (s->cap == 0) return;
+  if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film) return;
   WaveBuffers w;
   w.device = s->device; w.cap = s->cap;
   w.state[0] = s->state[0]; w.state[1] = s->state[1]; w.hits = s->hits; w.shq = s->shq; w.rad = s->rad; w.defer_list = s->defer_list;
+  w.counters = s->counters; w.counters_len = s->counters_len; w.shadow_ref = s->shadow_ref; w.film = s->film; w.film_len = s->film_len;
   s->cap = 0;
   s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
+  s->counters = nullptr; s->counters_len = 0; s->shadow_ref = nullptr; s->film = nullptr; s->film_len = 0;
   std::lock_guard<std::mutex> lock(g_pool_mutex);
   for (WaveBuffers& p : g_pool)
     if (p.device == w.device) {
@@ -516,20 +538,30 @@ void release_wave_buffers(BnScene* s) {  // park the scene's buffers for the nex
   g_pool.push_back(w);
 }
 
+// Takes this device's parked bundle, if there is one (whatever its size: the caller grows what is too small).
+void adopt_parked_buffers(BnScene* s) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (size_t k = 0; k < g_pool.size(); ++k)
+    if (g_pool[k].device == s->device) {
+      const WaveBuffers w = g_pool[k];
+      g_pool.erase(g_pool.begin() + (long)k);
+      s->cap = w.cap;
+      s->state[0] = w.state[0]; s->state[1] = w.state[1]; s->hits = w.hits; s->shq = w.shq; s->rad = w.rad; s->defer_list = w.defer_list;
+      s->counters = w.counters; s->counters_len = w.counters_len; s->shadow_ref = w.shadow_ref; s->film = w.film; s->film_len = w.film_len;
+      return;
+    }
+}
+
 int ensure_wave_buffers(BnScene* s, size_t cap) {
   if (s->cap >= cap) return BN_OK;
-  release_wave_buffers(s);
-  {
-    std::lock_guard<std::mutex> lock(g_pool_mutex);
-    for (size_t k = 0; k < g_pool.size(); ++k)
-      if (g_pool[k].device == s->device && g_pool[k].cap >= cap) {
-        const WaveBuffers w = g_pool[k];
-        g_pool.erase(g_pool.begin() + (long)k);
-        s->cap = w.cap;
-        s->state[0] = w.state[0]; s->state[1] = w.state[1]; s->hits = w.hits; s->shq = w.shq; s->rad = w.rad; s->defer_list = w.defer_list;
-        return BN_OK;
-      }
+  if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film) {
+    adopt_parked_buffers(s);
+    if (s->cap >= cap) return BN_OK;
   }
+  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list})
+    if (p) cudaFree(p);
+  s->cap = 0;
+  s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
   BN_CUDA(cudaMalloc((void**)&s->state[0], cap * 3 * sizeof(float4)));
   BN_CUDA(cudaMalloc((void**)&s->state[1], cap * 3 * sizeof(float4)));
   BN_CUDA(cudaMalloc((void**)&s->hits, cap * sizeof(float4)));
@@ -593,6 +625,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
       BN_CUDA(cudaMalloc((void**)&s->counters, need * sizeof(int)));
       s->counters_len = need;
     }
+    if (!s->shadow_ref) BN_CUDA(cudaMalloc((void**)&s->shadow_ref, sizeof(unsigned long long)));
     BN_CUDA(cudaMemsetAsync(s->counters, 0, need * sizeof(int), stream));
     BN_CUDA(cudaMemsetAsync(s->shadow_ref, 0, sizeof(unsigned long long), stream));
     const int grid = s->num_sms * 8;
@@ -770,31 +803,28 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   std::string err;
   if (!bnconv::convert_scene(*desc, cs, err)) { bnhost::set_error(err); return BN_ERR_INVALID; }
   BN_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop{};
-  BN_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) { bnhost::set_error("device is not sm_100-class (this library is built for sm_100a only)"); return BN_ERR_NO_DEVICE; }
+  int cc_major = 0, sm_count = 0;  // (cudaGetDeviceProperties costs milliseconds per call; two attributes do not)
+  BN_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  BN_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major < 10) { bnhost::set_error("device is not sm_100-class (this library is built for sm_100a only)"); return BN_ERR_NO_DEVICE; }
   auto* s = new BnScene();
   s->device = device;
-  s->num_sms = prop.multiProcessorCount;
+  s->num_sms = sm_count;
   int rc = BN_OK;
   DScene& d = s->d;
-  if ((rc = upload(s, cs.nodes, &d.nodes)) || (rc = upload(s, cs.inst_trav, &d.inst_trav)) || (rc = upload(s, cs.inst_head, &d.inst_head)) || (rc = upload(s, cs.inst_w2o, &d.inst_w2o)) ||
-      (rc = upload(s, cs.inst_o2w, &d.inst_o2w)) || (rc = upload(s, cs.meshes, &d.meshes)) || (rc = upload(s, cs.tris, &d.tris)) ||
-      (rc = upload(s, cs.alias, &d.alias)) || (rc = upload(s, cs.sphere_radii, &d.sphere_radii)) || (rc = upload(s, cs.materials, &d.materials)) ||
-      (rc = upload(s, cs.lights, &d.lights)) || (rc = upload(s, cs.light_inst, &d.light_inst))) {
-    bn_scene_destroy(s);
-    return rc;
-  }
+  // every scene array in ONE device allocation, filled by ONE host -> device copy
+  SceneArena arena;
+  arena.add(cs.nodes, &d.nodes); arena.add(cs.inst_trav, &d.inst_trav); arena.add(cs.inst_head, &d.inst_head); arena.add(cs.inst_w2o, &d.inst_w2o);
+  arena.add(cs.inst_o2w, &d.inst_o2w); arena.add(cs.meshes, &d.meshes); arena.add(cs.tris, &d.tris); arena.add(cs.alias, &d.alias);
+  arena.add(cs.sphere_radii, &d.sphere_radii); arena.add(cs.materials, &d.materials); arena.add(cs.lights, &d.lights); arena.add(cs.light_inst, &d.light_inst);
+  d.flat_tlas = nullptr;
+  if (!cs.flat_tlas.empty() && !std::getenv("BN_NO_FLAT_TLAS")) arena.add(cs.flat_tlas, &d.flat_tlas);
+  if ((rc = arena.commit(s))) { bn_scene_destroy(s); return rc; }
   d.tlas = cs.tlas;
   d.n_inst = (uint32_t)cs.inst_head.size();
   d.n_light_inst = (uint32_t)cs.light_inst.size();
   d.all_finite = cs.all_finite ? 1u : 0u;
-  d.flat_tlas = nullptr;
-  if (!cs.flat_tlas.empty() && !std::getenv("BN_NO_FLAT_TLAS")) {
-    if ((rc = upload(s, cs.flat_tlas, &d.flat_tlas))) { bn_scene_destroy(s); return rc; }
-  }
   d.cam = cs.cam;
-  if (cudaMalloc((void**)&s->shadow_ref, sizeof(unsigned long long)) != cudaSuccess) { bn_scene_destroy(s); bnhost::set_error("cudaMalloc failed"); return BN_ERR_CUDA; }
   *out = s;
   return BN_OK;
 }
@@ -804,9 +834,7 @@ void bn_scene_destroy(BnScene* s) {
   cudaSetDevice(s->device);
   for (void* p : s->allocs) cudaFree(p);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
-  release_wave_buffers(s);
-  for (void* p : {(void*)s->counters, (void*)s->shadow_ref, (void*)s->film})
-    if (p) cudaFree(p);
+  release_wave_buffers(s);  // parks the wave, counter and film buffers for the next scene on this device
   delete s;
 }
 
@@ -823,6 +851,7 @@ int bn_render(BnScene* s, const BnRenderParams* p, float* film, BnStats* stats) 
   if (rc != BN_OK) return rc;
   BN_CUDA(cudaSetDevice(s->device));
   const size_t len = (size_t)p->width * p->height * 3;
+  if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film) adopt_parked_buffers(s);
   if (s->film_len < len) {
     if (s->film) cudaFree(s->film);
     s->film = nullptr; s->film_len = 0;
