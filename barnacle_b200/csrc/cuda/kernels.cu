@@ -835,6 +835,9 @@ void bn_scene_destroy(BnScene* s) {
   for (void* p : s->allocs) cudaFree(p);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
   release_wave_buffers(s);  // parks the wave, counter and film buffers for the next scene on this device
+  for (void* p : {(void*)s->mlt_f, (void*)s->mlt_i, (void*)s->mlt_w, (void*)s->mlt_cnt, (void*)s->mlt_acc})
+    if (p) cudaFree(p);
+  if (s->mlt_w_host) cudaFreeHost(s->mlt_w_host);
   delete s;
 }
 

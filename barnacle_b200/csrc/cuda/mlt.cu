@@ -343,18 +343,38 @@ int validate(const BnScene* s, const BnMltParams* p) {
   return BN_OK;
 }
 
-struct MltBuffers {
-  float* f = nullptr;  // value | backup
-  int* i = nullptr;    // last_mod | mod_backup
-  ~MltBuffers() { if (f) cudaFree(f); if (i) cudaFree(i); }
-  int alloc(size_t n_threads, int xs_len, MltState& st) {
-    const size_t n = n_threads * (size_t)xs_len;
-    MLT_CUDA(cudaMalloc((void**)&f, 2 * n * sizeof(float)));
-    MLT_CUDA(cudaMalloc((void**)&i, 2 * n * sizeof(int)));
-    st.value = f; st.backup = f + n; st.last_mod = i; st.mod_backup = i + n;
-    return BN_OK;
+// Scratch owned by the scene and reused by every render (no allocation in the steady state).
+int ensure_mlt_state(BnScene* s, size_t n_threads, int xs_len, MltState& st) {
+  const size_t n = n_threads * (size_t)xs_len;
+  if (s->mlt_len < n) {
+    if (s->mlt_f) cudaFree(s->mlt_f);
+    if (s->mlt_i) cudaFree(s->mlt_i);
+    s->mlt_f = nullptr; s->mlt_i = nullptr; s->mlt_len = 0;
+    MLT_CUDA(cudaMalloc((void**)&s->mlt_f, 2 * n * sizeof(float)));
+    MLT_CUDA(cudaMalloc((void**)&s->mlt_i, 2 * n * sizeof(int)));
+    s->mlt_len = n;
   }
-};
+  st.value = s->mlt_f; st.backup = s->mlt_f + n; st.last_mod = s->mlt_i; st.mod_backup = s->mlt_i + n;
+  return BN_OK;
+}
+int ensure_mlt_misc(BnScene* s, size_t n_weights, size_t n_acc) {
+  if (!s->mlt_cnt) MLT_CUDA(cudaMalloc((void**)&s->mlt_cnt, 4 * sizeof(unsigned long long)));
+  if (s->mlt_w_len < n_weights) {
+    if (s->mlt_w) cudaFree(s->mlt_w);
+    if (s->mlt_w_host) cudaFreeHost(s->mlt_w_host);
+    s->mlt_w = nullptr; s->mlt_w_host = nullptr; s->mlt_w_len = 0;
+    MLT_CUDA(cudaMalloc((void**)&s->mlt_w, n_weights * sizeof(float)));
+    MLT_CUDA(cudaMallocHost((void**)&s->mlt_w_host, n_weights * sizeof(float)));
+    s->mlt_w_len = n_weights;
+  }
+  if (s->mlt_acc_len < n_acc) {
+    if (s->mlt_acc) cudaFree(s->mlt_acc);
+    s->mlt_acc = nullptr; s->mlt_acc_len = 0;
+    MLT_CUDA(cudaMalloc((void**)&s->mlt_acc, n_acc * sizeof(unsigned int)));
+    s->mlt_acc_len = n_acc;
+  }
+  return BN_OK;
+}
 
 MltParams device_params(const BnMltParams* p) {
   MltParams d{};
@@ -365,35 +385,31 @@ MltParams device_params(const BnMltParams* p) {
   return d;
 }
 
-// phase 1 on the device; weights_host receives BootstrapWeights
-int run_bootstrap(BnScene* s, const BnMltParams* p, cudaStream_t stream, std::vector<float>& weights_host, uint64_t& rays, double& ms) {
+// phase 1 on the device; *weights_host points at BootstrapWeights (pinned, owned by the scene)
+int run_bootstrap(BnScene* s, const BnMltParams* p, cudaStream_t stream, const float** weights_host, uint64_t& rays, double& ms) {
   MltParams dp = device_params(p);
   const int threads = std::min<long long>((long long)s->num_sms * 16 * 128, ((long long)p->n_bootstrap + 127) / 128 * 128);
   dp.n_threads = threads;
-  MltBuffers buf;
   MltState st{};
-  int rc = buf.alloc((size_t)threads, dp.xs_len, st);
+  int rc = ensure_mlt_state(s, (size_t)threads, dp.xs_len, st);
   if (rc != BN_OK) return rc;
-  float* d_w = nullptr;
-  unsigned long long* d_rays = nullptr;
-  MLT_CUDA(cudaMalloc((void**)&d_w, sizeof(float) * (size_t)p->n_bootstrap));
-  MLT_CUDA(cudaMalloc((void**)&d_rays, sizeof(unsigned long long)));
+  if ((rc = ensure_mlt_misc(s, (size_t)p->n_bootstrap, 0)) != BN_OK) return rc;
+  unsigned long long* d_rays = s->mlt_cnt + 3;
   MLT_CUDA(cudaMemsetAsync(d_rays, 0, sizeof(unsigned long long), stream));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, stream);
-  k_mlt_bootstrap<<<threads / 128, 128, 0, stream>>>(s->d, dp, st, d_w, d_rays);
+  k_mlt_bootstrap<<<threads / 128, 128, 0, stream>>>(s->d, dp, st, s->mlt_w, d_rays);
   cudaEventRecord(e1, stream);
-  weights_host.resize((size_t)p->n_bootstrap);
-  cudaError_t e = cudaMemcpyAsync(weights_host.data(), d_w, sizeof(float) * (size_t)p->n_bootstrap, cudaMemcpyDeviceToHost, stream);
+  cudaError_t e = cudaMemcpyAsync(s->mlt_w_host, s->mlt_w, sizeof(float) * (size_t)p->n_bootstrap, cudaMemcpyDeviceToHost, stream);
   unsigned long long r = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&r, d_rays, sizeof r, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   float t = 0.f;
   if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(d_w); cudaFree(d_rays);
   if (e != cudaSuccess) { s->poisoned = true; ok(e, "pssmlt bootstrap"); return BN_ERR_CUDA; }
+  *weights_host = s->mlt_w_host;
   rays = r; ms = t;
   return BN_OK;
 }
@@ -402,13 +418,13 @@ int render_pssmlt(BnScene* s, const BnMltParams* p, float* d_film, cudaStream_t 
   int rc = validate(s, p);
   if (rc != BN_OK) return rc;
   MLT_CUDA(cudaSetDevice(s->device));
-  std::vector<float> w;
+  const float* w = nullptr;
   uint64_t rays_boot = 0;
   double ms_boot = 0;
-  rc = run_bootstrap(s, p, stream, w, rays_boot, ms_boot);
+  rc = run_bootstrap(s, p, stream, &w, rays_boot, ms_boot);
   if (rc != BN_OK) return rc;
   float sum = 0.f;
-  for (float x : w) sum = sum + x;  // Array.average (PSSMLT.fs:394): sequential fp32 sum / n, on the host
+  for (int k = 0; k < p->n_bootstrap; ++k) sum = sum + w[k];  // Array.average (PSSMLT.fs:394): sequential fp32 sum / n, on the host
   const float B = sum / (float)p->n_bootstrap;
   BnMltStats out{};
   out.b = B; out.rays = rays_boot; out.bootstrap_ms = ms_boot;
@@ -420,15 +436,13 @@ int render_pssmlt(BnScene* s, const BnMltParams* p, float* d_film, cudaStream_t 
     dp.inv_b = 1.0f / B;
     const int threads = (n_run + 127) / 128 * 128;
     dp.n_threads = threads;
-    MltBuffers buf;
     MltState st{};
-    rc = buf.alloc((size_t)threads, dp.xs_len, st);
+    rc = ensure_mlt_state(s, (size_t)threads, dp.xs_len, st);
     if (rc != BN_OK) return rc;
-    unsigned long long* d_cnt = nullptr;
-    unsigned int* d_acc = nullptr;
-    MLT_CUDA(cudaMalloc((void**)&d_cnt, 3 * sizeof(unsigned long long)));
+    if ((rc = ensure_mlt_misc(s, (size_t)p->n_bootstrap, per_chain_host ? (size_t)threads : 0)) != BN_OK) return rc;
+    unsigned long long* d_cnt = s->mlt_cnt;
+    unsigned int* d_acc = per_chain_host ? s->mlt_acc : nullptr;
     MLT_CUDA(cudaMemsetAsync(d_cnt, 0, 3 * sizeof(unsigned long long), stream));
-    if (per_chain_host) MLT_CUDA(cudaMalloc((void**)&d_acc, sizeof(unsigned int) * (size_t)threads));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, stream);
@@ -441,8 +455,6 @@ int render_pssmlt(BnScene* s, const BnMltParams* p, float* d_film, cudaStream_t 
     float t = 0.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_cnt);
-    if (d_acc) cudaFree(d_acc);
     if (e != cudaSuccess) { s->poisoned = true; ok(e, "pssmlt chains"); return BN_ERR_CUDA; }
     out.rays += cnt[0]; out.accepted = cnt[1]; out.proposed = cnt[2]; out.chains_ms = t;
   }
@@ -459,11 +471,11 @@ int bn_pssmlt_bootstrap(BnScene* s, const BnMltParams* p, float* weights) {
   int rc = validate(s, p);
   if (rc != BN_OK) return rc;
   MLT_CUDA(cudaSetDevice(s->device));
-  std::vector<float> w;
+  const float* w = nullptr;
   uint64_t rays = 0;
   double ms = 0;
-  rc = run_bootstrap(s, p, nullptr, w, rays, ms);
-  if (rc == BN_OK) std::copy(w.begin(), w.end(), weights);
+  rc = run_bootstrap(s, p, nullptr, &w, rays, ms);
+  if (rc == BN_OK) std::copy(w, w + p->n_bootstrap, weights);
   return rc;
 }
 

@@ -25,6 +25,17 @@ struct BnScene {
   unsigned long long* shadow_ref = nullptr;
   float* film = nullptr;
   size_t film_len = 0;
+  // PSSMLT scratch (mlt.cu), grown on demand and kept for the scene's lifetime: primary-sample
+  // arrays, bootstrap weights (device + pinned host), counters
+  float* mlt_f = nullptr;
+  int* mlt_i = nullptr;
+  size_t mlt_len = 0;            // elements of each of the 2+2 primary-sample arrays
+  float* mlt_w = nullptr;
+  float* mlt_w_host = nullptr;   // pinned
+  size_t mlt_w_len = 0;
+  unsigned long long* mlt_cnt = nullptr;  // 4 counters
+  unsigned int* mlt_acc = nullptr;
+  size_t mlt_acc_len = 0;
   bool poisoned = false;
   std::vector<cudaEvent_t> events;  // BN_RENDER_PROFILE: start/stop pairs, one per kernel launch
 };
