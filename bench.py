@@ -236,7 +236,7 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
             "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12, "ms_per_step": e2e_s / args.steps * 1e3},
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_mlt_chains (one Markov chain per thread)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "first implementation of the next row: per-thread megakernel on the exact traversal; not yet profiled against a roofline"},
+                         "note": "per-thread megakernel on the exact per-lane traversal (divergence- and latency-bound, scene in L2); no bytes-per-mutation roofline is claimed for this row"},
             "cpu_baseline": None}))
     if world > 1:
         dist.destroy_process_group()
@@ -415,11 +415,12 @@ def main():
                               "peak_source": "bn_measure_l2_read_gbs: 20 sweeps of a 32 MiB L2-resident buffer, ld.global.cg.v4, CUDA events, this run"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            # ~10-30 s of CPU work: 4 spp of the workload's film (libm math, as the reference)
-            cs = oracle_sample(scene, W, H, 4 if W * H <= (1 << 21) else 1, False)
+            # ~10-30 s of CPU work on all host threads: about 30 M paths of the workload's film (libm math, as the reference)
+            cpu_spp = max(1, min(SPP, -(-30_000_000 // (W * H))))
+            cs = oracle_sample(scene, W, H, cpu_spp, False)
             cpu = {"value": (cs["extend_rays"] + cs["shadow_rays"]) / cs["seconds"] / 1e6, "unit": "Mrays/s", "cores": cs["threads"], "kind": "port",
                    "samples_per_s": cs["paths"] / cs["seconds"],
-                   "sample": f"{W}x{H} at {4 if W * H <= (1 << 21) else 1} of {SPP} spp ({cs['seconds']:.1f} s); rays = extend + shadow rays the reference traces",
+                   "sample": f"{W}x{H} at {cpu_spp} of {SPP} spp ({cs['seconds']:.1f} s); rays = extend + shadow rays the reference traces",
                    "note": "C++ restatement of Barnacle's CPU path (the .NET binary is not runnable in this image)"}
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -48,3 +48,30 @@ def test_last_error_and_bad_args(lib):
     assert rc == _ffi.BN_ERR_IO and b"cannot open" in lib.bn_last_error()
     rc = lib.bn_host_scene_load_string(b'{"nodes": [', None, 0.0, ctypes.byref(h))
     assert rc == _ffi.BN_ERR_IO and b"JSON" in lib.bn_last_error()
+
+
+def test_device_entry_points_fail_loudly_without_a_gpu(lib):
+    """bn_bvh_build / bn_measure_l2_read_gbs have no host fallback either."""
+    if lib.bn_device_count() > 0:
+        return
+    import numpy as np
+    boxes = np.array([[0, 0, 0, 1, 1, 1]] * 8, dtype=np.float32)
+    nodes = (_ffi.BnBVHNode * 16)()
+    rc = lib.bn_bvh_build(0, boxes.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 8, nodes, 16, None, None)
+    assert rc == _ffi.BN_ERR_NO_DEVICE and b"no CUDA device" in lib.bn_last_error()
+    gbs = ctypes.c_double(0)
+    assert lib.bn_measure_l2_read_gbs(0, 32 << 20, 4, ctypes.byref(gbs)) == _ffi.BN_ERR_NO_DEVICE
+
+
+def test_scene_load_ex_with_host_builder_equals_scene_load(lib, root):
+    """bn_host_scene_load_ex(build_device = -1) is bn_host_scene_load."""
+    import os
+    from barnacle_b200.scene import Scene
+    path = os.path.join(root, "scenes", "cbox_pt.json")
+    a = Scene.Load(path, base_dir=root)
+    b = Scene.Load(path, base_dir=root, build_device=-1)
+    da, db = a.desc.contents, b.desc.contents
+    assert da.tlas_node_count == db.tlas_node_count and da.instance_count == db.instance_count
+    assert ctypes.string_at(da.tlas_nodes, da.tlas_node_count * 32) == ctypes.string_at(db.tlas_nodes, db.tlas_node_count * 32)
+    assert ctypes.string_at(da.instances, da.instance_count * 168) == ctypes.string_at(db.instances, db.instance_count * 168)
+    b.close()
