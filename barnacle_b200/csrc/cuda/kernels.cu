@@ -44,6 +44,9 @@ constexpr int kBlock = 128;
 #ifndef BN_SHADE_MIN_BLOCKS
 #define BN_SHADE_MIN_BLOCKS 6
 #endif
+#ifndef BN_COUNTER_STRIDE
+#define BN_COUNTER_STRIDE 64   // ints between two queue counters / cursors (256 B)
+#endif
 #ifndef BN_TRAV_GRID_MULT
 #define BN_TRAV_GRID_MULT 8    // persistent grid = SMs x this
 #endif
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
                                                   float4* __restrict__ q2, float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr,
                                                   int* n_out, int* n_shadow, int* cursor, unsigned long long* shadow_ref) {
   const int n = *n_ptr;
+  unsigned ref_total = 0;  // lane 0: reference-equivalent shadow rays of this warp's chunks
   int next = warp_fetch(cursor);
   for (;;) {
     const int base = next;
@@ -294,9 +298,9 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
       q2[spos] = make_float4(sh_a.x, sh_a.y, sh_a.z, sh_b.x);
       q3[spos] = make_float4(sh_b.y, sh_b.z, 0.f, 0.f);
     }
-    const unsigned rm = __ballot_sync(0xffffffffu, ref_shadow);
-    if (lane_id() == 0 && rm) atomicAdd(shadow_ref, (unsigned long long)__popc(rm));
+    ref_total += (unsigned)__popc(__ballot_sync(0xffffffffu, ref_shadow));
   }
+  if (lane_id() == 0 && ref_total) atomicAdd(shadow_ref, (unsigned long long)ref_total);
 }
 
 // ---- shadow: any hit + connect (PathTracing.fs:47-59) ----------------------------------
@@ -617,7 +621,11 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     const long long n_waves = n_block_chunks * n_sample_chunks;
     // per wave: n_active(bounce 0..maxDepth) | n_shadow(bounce) | cursors 3 per bounce | deferred counts 2 per bounce
     const int D = D_bounces;
-    const size_t per_wave = (size_t)(D + 1) + D + 3 * (size_t)D + 2 * (size_t)D;
+    // Every counter sits in its own 256-B slot: the kernels of one bounce hammer three or four of them
+    // with one atomic per warp per 32 paths, and atomics that share a cache line are serialised by
+    // the L2 slice that owns the line (BN_COUNTER_STRIDE ints apart = different lines / slices).
+    constexpr size_t CS = BN_COUNTER_STRIDE;
+    const size_t per_wave = ((size_t)(D + 1) + D + 3 * (size_t)D + 2 * (size_t)D) * CS;
     const size_t need = per_wave * (size_t)n_waves;
     if (s->counters_len < need) {
       if (s->counters) cudaFree(s->counters);
@@ -668,10 +676,10 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         wp.inv_spp = 1.0f / (float)p->spp;  // MathF.ReciprocalEstimate restated as IEEE 1/x
         wp.il_count = il_count; wp.il_index = il_index;
         int* base = s->counters + per_wave * (size_t)wave;
-        int* n_active = base;
-        int* n_shadow = base + (D + 1);
-        int* cursors = base + (D + 1) + D;
-        int* n_defer = cursors + 3 * D;
+        int* n_active = base;                               // [b] at n_active + b * CS, and so on
+        int* n_shadow = base + (size_t)(D + 1) * CS;
+        int* cursors = base + (size_t)((D + 1) + D) * CS;
+        int* n_defer = cursors + (size_t)(3 * D) * CS;
         const size_t cp = s->cap;
         float4* A = s->state[0];
         float4* B = s->state[1];
@@ -681,17 +689,17 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         ++launches;
         for (int b = 0; b < D; ++b) {
           prof_begin(0);
-          const ExtendIO eio{A, A + cp, s->hits, n_active + b, cursors + 3 * b, DeferList{n_defer + 2 * b, s->defer_list}};
+          const ExtendIO eio{A, A + cp, s->hits, n_active + b * CS, cursors + (3 * b) * CS, DeferList{n_defer + (2 * b) * CS, s->defer_list}};
           k_traverse<false, ExtendIO><<<tgrid, kBlock, 0, stream>>>(dsc, eio);
           k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
           prof_end();
           prof_begin(1);
           k_shade<<<grid, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
-                                               s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b, n_active + b + 1, n_shadow + b,
-                                               cursors + 3 * b + 1, s->shadow_ref);
+                                               s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b * CS, n_active + (b + 1) * CS, n_shadow + b * CS,
+                                               cursors + (3 * b + 1) * CS, s->shadow_ref);
           prof_end();
           prof_begin(2);
-          const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b, cursors + 3 * b + 2, DeferList{n_defer + 2 * b + 1, s->defer_list}};
+          const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b * CS, cursors + (3 * b + 2) * CS, DeferList{n_defer + (2 * b + 1) * CS, s->defer_list}};
           k_traverse<true, ShadowIO><<<tgrid, kBlock, 0, stream>>>(dsc, sio);
           k_traverse_fixup<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
           prof_end();
@@ -716,7 +724,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
       for (long long w = 0; w < n_waves; ++w) {
         const int* base = h_counters.data() + per_wave * (size_t)w;
         n_paths += (uint64_t)base[0];
-        for (int b = 0; b < D; ++b) { ext += (uint64_t)base[b]; sh += (uint64_t)base[D + 1 + b]; }
+        for (int b = 0; b < D; ++b) { ext += (uint64_t)base[(size_t)b * CS]; sh += (uint64_t)base[(size_t)(D + 1 + b) * CS]; }
       }
       unsigned long long ref = 0;
       BN_CUDA(cudaMemcpy(&ref, s->shadow_ref, sizeof ref, cudaMemcpyDeviceToHost));

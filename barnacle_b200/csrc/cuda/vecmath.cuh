@@ -27,7 +27,18 @@ BN_DEV float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
 BN_DEV float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 BN_DEV float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
 BN_DEV float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
-BN_DEV float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+// a / s, IEEE round-to-nearest (what `/` compiles to here), with one case kept off nvcc's slow path:
+// a zero numerator fails the FCHK range test and sends the whole warp through the out-of-line
+// special-case routine, and axis-aligned geometry (Cornell-box normals and tangents) puts exact
+// zeros into every normalize().  0 / s for a normal finite s is +-0 with the XOR of the signs, so
+// that case is answered directly and the divider only ever sees a non-zero numerator.
+BN_DEV float div_ieee(float a, float s) {
+  const float as = fabsf(s);
+  const bool zero_num = a == 0.f && as >= 1.17549435e-38f && as <= 3.402823466e38f;
+  const float q = (zero_num ? 1.f : a) / s;
+  return zero_num ? __uint_as_float((__float_as_uint(a) ^ __float_as_uint(s)) & 0x80000000u) : q;
+}
+BN_DEV float3 operator/(float3 a, float s) { return f3(div_ieee(a.x, s), div_ieee(a.y, s), div_ieee(a.z, s)); }
 // Vector3.FusedMultiplyAdd
 BN_DEV float3 vfma(float3 a, float3 b, float3 c) { return f3(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y), __fmaf_rn(a.z, b.z, c.z)); }
 // Vector3.Dot: ((x*x' + y*y') + z*z')
