@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(kBlock) k_raygen(DScene sc, WaveParams wp, flo
   }
 }
 
+BN_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- extend: closest hit for every live path ----------------------------------------
 struct DeferList {  // rays that need the exact traversal (fix-up kernel)
   int* count;
@@ -149,6 +151,7 @@ struct ExtendIO {
     hits[i] = make_float4(r.t, __int_as_float(r.inst), __int_as_float(r.prim), 0.f);
   }
   BN_DEV void defer(int i) const { deferred.push(i); }
+  BN_DEV void prefetch(int i) const { prefetch_l2(s0 + i); prefetch_l2(s1 + i); }
 };
 template <bool ANY, class IO>
 __global__ void __launch_bounds__(kBlock, BN_TRAV_MIN_BLOCKS) k_traverse(DScene sc, IO io) {
@@ -172,6 +175,10 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
     const int base = next;
     if (base >= n) break;
     next = warp_fetch(cursor);  // claimed one chunk ahead: the atomic's round trip overlaps this chunk's shading
+    if (next + lane_id() < n) {  // ... and so does the DRAM latency of its inputs
+      const int j = next + lane_id();
+      prefetch_l2(s0 + j); prefetch_l2(s1 + j); prefetch_l2(s2 + j); prefetch_l2(hits + j);
+    }
     const int i = base + lane_id();
     bool alive = false, has_shadow = false, ref_shadow = false;
     float3 P = splat(0.f), nd = splat(0.f), beta = splat(0.f);
@@ -319,7 +326,10 @@ struct ShadowIO {
     const float4 a = q0[i], b = q1[i];
     o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
     t = b.z;
+    // what store() reads if the ray turns out unoccluded: in L2 by the time the traversal is done
+    prefetch_l2(q2 + i); prefetch_l2(q3 + i); prefetch_l2(rad + __float_as_int(b.w));
   }
+  BN_DEV void prefetch(int i) const { prefetch_l2(q0 + i); prefetch_l2(q1 + i); }
   BN_DEV void store(int i, const TraceResult& r) const {
     if (r.hit) return;  // occluded
     const float4 b = q1[i], c = q2[i], e = q3[i];
@@ -394,6 +404,7 @@ struct TraceIO {
   BN_DEV int count() const { return n; }
   BN_DEV int* cursor() const { return cur; }
   BN_DEV void defer(int i) const { deferred.push(i); }
+  BN_DEV void prefetch(int i) const { prefetch_l2(rays + i); }
   BN_DEV void load(int i, float3& o, float3& d, float& t) const {
     const BnRay r = rays[i];
     o = f3(r.origin[0], r.origin[1], r.origin[2]); d = f3(r.direction[0], r.direction[1], r.direction[2]);

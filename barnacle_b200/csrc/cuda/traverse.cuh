@@ -50,6 +50,10 @@ constexpr int kRefillMin = BN_REFILL_MIN;  // refill when at least this many lan
 #ifndef BN_STAY_MIN
 #define BN_STAY_MIN 12
 #endif
+#ifndef BN_PREFETCH_AHEAD
+#define BN_PREFETCH_AHEAD 16384
+#endif
+constexpr int kPrefetchAhead = BN_PREFETCH_AHEAD;  // queue entries between a refill's loads and its L2 prefetches
 constexpr int kStayMin = BN_STAY_MIN;      // phase N repeats without a vote while at least this many lanes are at a node (33: never)
 
 #ifdef BN_TRAV_STATS
@@ -194,6 +198,7 @@ BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, floa
 //              void load(int i, float3& o, float3& d, float& tmax) ;
 //              void store(int i, const TraceResult&) ;
 //              void defer(int i)      // ray i needs the exact path (fix-up kernel)
+//              void prefetch(int i)   // hint: ray i will be loaded soon (L2 prefetch)
 // ---------------------------------------------------------------------------------
 template <bool ANY, class IO>
 BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
@@ -273,6 +278,10 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
       const int mine = base + __popc(idle & lt_mask);
       if (cur == kNone && mine < n) {
         index = mine;
+        // Claims tile the queue in increasing order, so "my slot + kPrefetchAhead" is a ray some
+        // warp will claim about a DRAM latency from now: every refill pulls its share of that
+        // future window into L2.
+        if (mine + kPrefetchAhead < n) io.prefetch(mine + kPrefetchAhead);
         io.load(mine, wo, wd, t);
         winv = rcp3(wd);
         wsigns = dir_signs(wd);
