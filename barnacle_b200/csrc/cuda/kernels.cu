@@ -39,7 +39,7 @@ namespace bn {
 
 constexpr int kBlock = 128;
 #ifndef BN_TRAV_MIN_BLOCKS
-#define BN_TRAV_MIN_BLOCKS 8   // resident CTAs per SM the traversal kernels are compiled for (register cap)
+#define BN_TRAV_MIN_BLOCKS 9   // resident CTAs per SM the traversal kernels are compiled for (56 registers: the cold per-ray state is in shared memory)
 #endif
 #ifndef BN_SHADE_MIN_BLOCKS
 #define BN_SHADE_MIN_BLOCKS 6
@@ -48,7 +48,7 @@ constexpr int kBlock = 128;
 #define BN_COUNTER_STRIDE 64   // ints between two queue counters / cursors (256 B)
 #endif
 #ifndef BN_TRAV_GRID_MULT
-#define BN_TRAV_GRID_MULT 8    // persistent grid = SMs x this
+#define BN_TRAV_GRID_MULT 9    // persistent grid = SMs x this
 #endif
 
 struct WaveParams {
@@ -155,7 +155,8 @@ struct ExtendIO {
 };
 template <bool ANY, class IO>
 __global__ void __launch_bounds__(kBlock, BN_TRAV_MIN_BLOCKS) k_traverse(DScene sc, IO io) {
-  traverse_persistent<ANY>(sc, io);
+  __shared__ uint32_t s_cold[kTravColdWords * kBlock];
+  traverse_persistent<ANY>(sc, io, s_cold + threadIdx.x, kBlock);
 }
 template <bool ANY, class IO>
 __global__ void __launch_bounds__(kBlock) k_traverse_fixup(DScene sc, IO io) {

@@ -200,25 +200,37 @@ BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, floa
 //              void defer(int i)      // ray i needs the exact path (fix-up kernel)
 //              void prefetch(int i)   // hint: ray i will be loaded soon (L2 prefetch)
 // ---------------------------------------------------------------------------------
+// `cold`: this thread's column of a [kTravColdWords][blockDim.x] shared-memory array.  The state a
+// ray touches a few times in its life (committed hit, queue slot, world direction, candidate mask)
+// lives there instead of in registers; that is what lets the kernel fit 9 CTAs per SM.
+constexpr int kTravColdWords = 9;
 template <bool ANY, class IO>
-BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
+BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__ cold, const int cold_stride) {
   uint2 stk[kStackSize];  // (ref, entry distance bits)
   // per-lane state
-  float3 wo, wd, winv;    // world-space ray
+  float3 wo, winv;        // world-space ray (origin, 1/direction)
   float3 o, d, inv;       // ray in the CURRENT space
   float t = 0.f;          // closest distance so far (ANY: the fixed tmax)
-  int h_inst = -1, h_prim = -1;
-  float h_u = 0.f, h_v = 0.f;
+  int& h_inst = reinterpret_cast<int*>(cold)[0];
+  int& h_prim = reinterpret_cast<int*>(cold)[cold_stride];
+  float& h_u = reinterpret_cast<float*>(cold)[2 * cold_stride];
+  float& h_v = reinterpret_cast<float*>(cold)[3 * cold_stride];
+  float& wdx = reinterpret_cast<float*>(cold)[4 * cold_stride];
+  float& wdy = reinterpret_cast<float*>(cold)[5 * cold_stride];
+  float& wdz = reinterpret_cast<float*>(cold)[6 * cold_stride];
+  h_inst = -1; h_prim = -1; h_u = 0.f; h_v = 0.f;
   uint32_t cur = kNone;   // ref being processed; kScan: next instance of the flat TLAS; kNone: lane idle
   uint32_t signs = 8u;    // dir_signs of the current-space direction
   uint32_t wsigns = 8u;   // ... of the world-space direction
   int sp = 0;
   int cur_inst = -1;
-  int index = 0;          // queue slot of this ray
+  int& index = reinterpret_cast<int*>(cold)[7 * cold_stride];  // queue slot of this ray
   uint32_t tri_k = 0;     // next triangle of the held BLAS leaf
-  uint32_t tl_pos = 0;    // small TLAS: bit mask of the candidate instances still to visit (visiting order)
+  uint32_t& tl_pos = cold[8 * cold_stride];  // small TLAS: bit mask of the candidate instances still to visit (visiting order)
   bool in_obj = false;
-  wo = wd = winv = o = d = inv = splat(0.f);
+  index = 0; tl_pos = 0u;
+  wdx = wdy = wdz = 0.f;
+  wo = winv = o = d = inv = splat(0.f);
 
 #ifdef BN_TRAV_STATS
   unsigned long long st_cnt[5] = {0, 0, 0, 0, 0}, st_sum[5] = {0, 0, 0, 0, 0};
@@ -251,8 +263,8 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
       const uint2 e = stk[sp];
       if (ANY || __uint_as_float(e.y) <= t) { cur = e.x; break; }
     }
-    if ((cur & kTlasBit) && in_obj) {  // tree TLAS: back from a BLAS, restore the world-space ray
-      o = wo; d = wd; inv = winv;
+    if ((cur & kTlasBit) && in_obj) {  // tree TLAS: back from a BLAS, restore the world-space ray (d is only read inside a BLAS)
+      o = wo; inv = winv;
       signs = wsigns;
       in_obj = false;
     }
@@ -282,7 +294,9 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
         // warp will claim about a DRAM latency from now: every refill pulls its share of that
         // future window into L2.
         if (mine + kPrefetchAhead < n) io.prefetch(mine + kPrefetchAhead);
+        float3 wd;
         io.load(mine, wo, wd, t);
+        wdx = wd.x; wdy = wd.y; wdz = wd.z;
         winv = rcp3(wd);
         wsigns = dir_signs(wd);
         o = wo; d = wd; inv = winv; signs = wsigns;
@@ -380,7 +394,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
         tri_k = 0;
         if (fbits(m2.w)) {
           // identity mesh instance: object space == world space, root box == instance box (passed)
-          o = wo; d = wd; inv = winv; signs = wsigns;
+          o = wo; d = f3(wdx, wdy, wdz); inv = winv; signs = wsigns;
           in_obj = true;
           cur_inst = (int)slot;
           cur = fbits(m0.w);
@@ -389,7 +403,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
         const Mat43 M = load_mat43(ip);
         const float4 m1 = __ldg(ip + 4);
         const float3 oo = transform_point(wo, M);  // Ray.Transform (Ray.fs:19-22)
-        const float3 od = transform_dir(wd, M);
+        const float3 od = transform_dir(f3(wdx, wdy, wdz), M);
         if (fbits(m2.y)) {
           float tp;
           const int root = sphere_test(m2.z, oo, od, t, tp);
@@ -434,7 +448,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io) {
             if (fbits(b.w) != kNone) {
               // identity mesh instance: what phase E would do (object space == world space, the BLAS
               // root box is this box), done here so that the ray goes straight to its N / T phase
-              o = wo; d = wd; inv = winv; signs = wsigns;
+              o = wo; d = f3(wdx, wdy, wdz); inv = winv; signs = wsigns;
               in_obj = true;
               cur_inst = (int)fbits(a.w);
               tri_k = 0;

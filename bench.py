@@ -210,7 +210,6 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
         ms += ev0.elapsed_time(ev1); rays += st.rays; muts += st.proposed; acc += st.accepted
     barrier()
     t_wall1 = time.time()
-    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None   # the sampler covers the timed region only
     host_film = torch.empty(W * H * 3, dtype=torch.float32).pin_memory()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -219,6 +218,8 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
             host_film.copy_(film)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # stopped only now (an exiting NVML client can stall the next CUDA calls); its report covers t_wall0..t_wall1, the timed region
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     agg = torch.tensor([ms, float(rays), float(muts), float(acc), e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = agg.clone()
@@ -316,7 +317,6 @@ def main():
             tot["render_ms"] += st.gpu_ms
     barrier()
     t_wall1 = time.time()
-    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None   # the sampler covers the timed region only
     # flush.zero_() is inside ev0..ev1; subtract nothing — it is ~0.1 ms of a multi-hundred-ms step and is reported in config
     my_ms = float(sum(step_ms))
     agg = torch.tensor([my_ms, tot["extend"], tot["shadow"], tot["paths"], tot["launches"]], dtype=torch.float64, device="cuda")
@@ -369,6 +369,8 @@ def main():
             e2e_rays += st2.extend_rays + st2.shadow_rays
     barrier()
     e2e_s = time.perf_counter() - t0
+    # stopped only now (an exiting NVML client can stall the next CUDA calls); its report covers t_wall0..t_wall1, the timed region
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     e2e_t = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = e2e_t.clone()
