@@ -42,7 +42,7 @@ constexpr int kBlock = 128;
 #define BN_TRAV_MIN_BLOCKS 9   // resident CTAs per SM the traversal kernels are compiled for (56 registers: the cold per-ray state is in shared memory)
 #endif
 #ifndef BN_SHADE_MIN_BLOCKS
-#define BN_SHADE_MIN_BLOCKS 6
+#define BN_SHADE_MIN_BLOCKS 7
 #endif
 #ifndef BN_COUNTER_STRIDE
 #define BN_COUNTER_STRIDE 64   // ints between two queue counters / cursors (256 B)
@@ -481,6 +481,8 @@ struct WaveBuffers {
   unsigned long long* shadow_ref = nullptr;
   float* film = nullptr;
   size_t film_len = 0;
+  void* arena = nullptr;   // the dead scene's array allocation, reused by the next scene if it is large enough
+  size_t arena_bytes = 0;
 };
 std::mutex g_pool_mutex;
 std::vector<WaveBuffers> g_pool;
@@ -494,6 +496,8 @@ bool cuda_ok(cudaError_t e, const char* what) {
   do {                                                 \
     if (!cuda_ok((call), #call)) return BN_ERR_CUDA;   \
   } while (0)
+
+void adopt_parked_buffers(BnScene* s);
 
 // Lays the scene arrays out in one staging buffer (256-B aligned slices) so that bn_scene_create
 // costs one cudaMalloc and one cudaMemcpy whatever the number of arrays.
@@ -510,9 +514,14 @@ struct SceneArena {
     fixes.push_back({reinterpret_cast<const void**>(out), off});
   }
   int commit(BnScene* s) {
-    void* p = nullptr;
-    BN_CUDA(cudaMalloc(&p, staging.size()));
-    s->allocs.push_back(p);
+    adopt_parked_buffers(s);  // a warm device hands over the previous scene's allocation (and its wave buffers)
+    if (s->arena_bytes < staging.size()) {
+      if (s->arena) cudaFree(s->arena);
+      s->arena = nullptr; s->arena_bytes = 0;
+      BN_CUDA(cudaMalloc(&s->arena, staging.size()));
+      s->arena_bytes = staging.size();
+    }
+    void* p = s->arena;
     BN_CUDA(cudaMemcpy(p, staging.data(), staging.size(), cudaMemcpyHostToDevice));
     for (const Fix& f : fixes) *f.out = static_cast<const unsigned char*>(p) + f.offset;
     return BN_OK;
@@ -529,17 +538,19 @@ size_t wave_capacity_paths() {
 }
 
 void free_wave_buffers(WaveBuffers& w) {
-  for (void* p : {(void*)w.state[0], (void*)w.state[1], (void*)w.hits, (void*)w.shq, (void*)w.rad, (void*)w.defer_list, (void*)w.counters, (void*)w.shadow_ref, (void*)w.film})
+  for (void* p : {(void*)w.state[0], (void*)w.state[1], (void*)w.hits, (void*)w.shq, (void*)w.rad, (void*)w.defer_list, (void*)w.counters, (void*)w.shadow_ref, (void*)w.film, w.arena})
     if (p) cudaFree(p);
   w = WaveBuffers();
 }
 
 void release_wave_buffers(BnScene* s) {  // park the scene's buffers for the next scene on this device
-  if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film) return;
+  if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film && !s->arena) return;
   WaveBuffers w;
   w.device = s->device; w.cap = s->cap;
   w.state[0] = s->state[0]; w.state[1] = s->state[1]; w.hits = s->hits; w.shq = s->shq; w.rad = s->rad; w.defer_list = s->defer_list;
   w.counters = s->counters; w.counters_len = s->counters_len; w.shadow_ref = s->shadow_ref; w.film = s->film; w.film_len = s->film_len;
+  w.arena = s->arena; w.arena_bytes = s->arena_bytes;
+  s->arena = nullptr; s->arena_bytes = 0;
   s->cap = 0;
   s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
   s->counters = nullptr; s->counters_len = 0; s->shadow_ref = nullptr; s->film = nullptr; s->film_len = 0;
@@ -564,16 +575,14 @@ void adopt_parked_buffers(BnScene* s) {
       s->cap = w.cap;
       s->state[0] = w.state[0]; s->state[1] = w.state[1]; s->hits = w.hits; s->shq = w.shq; s->rad = w.rad; s->defer_list = w.defer_list;
       s->counters = w.counters; s->counters_len = w.counters_len; s->shadow_ref = w.shadow_ref; s->film = w.film; s->film_len = w.film_len;
+      s->arena = w.arena; s->arena_bytes = w.arena_bytes;
       return;
     }
 }
 
 int ensure_wave_buffers(BnScene* s, size_t cap) {
   if (s->cap >= cap) return BN_OK;
-  if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film) {
-    adopt_parked_buffers(s);
-    if (s->cap >= cap) return BN_OK;
-  }
+
   for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list})
     if (p) cudaFree(p);
   s->cap = 0;
@@ -706,7 +715,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
           k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
           prof_end();
           prof_begin(1);
-          k_shade<<<grid, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
+          k_shade<<<s->num_sms * BN_SHADE_MIN_BLOCKS, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
                                                s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b * CS, n_active + (b + 1) * CS, n_shadow + b * CS,
                                                cursors + (3 * b + 1) * CS, s->shadow_ref);
           prof_end();
@@ -852,7 +861,6 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
 void bn_scene_destroy(BnScene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  for (void* p : s->allocs) cudaFree(p);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
   release_wave_buffers(s);  // parks the wave, counter and film buffers for the next scene on this device
   for (void* p : {(void*)s->mlt_f, (void*)s->mlt_i, (void*)s->mlt_w, (void*)s->mlt_cnt, (void*)s->mlt_acc})
@@ -874,7 +882,6 @@ int bn_render(BnScene* s, const BnRenderParams* p, float* film, BnStats* stats) 
   if (rc != BN_OK) return rc;
   BN_CUDA(cudaSetDevice(s->device));
   const size_t len = (size_t)p->width * p->height * 3;
-  if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film) adopt_parked_buffers(s);
   if (s->film_len < len) {
     if (s->film) cudaFree(s->film);
     s->film = nullptr; s->film_len = 0;

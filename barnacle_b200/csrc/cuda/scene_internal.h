@@ -12,7 +12,8 @@ struct BnScene {
   int device = 0;
   int num_sms = 0;
   DScene d{};
-  std::vector<void*> allocs;
+  void* arena = nullptr;     // every scene array, one allocation (parked with the wave buffers when the scene dies)
+  size_t arena_bytes = 0;
   // wave buffers
   size_t cap = 0;
   float4* state[2] = {nullptr, nullptr};  // 3 planes each

@@ -363,8 +363,11 @@ def main():
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
+    e2e_step_ms = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         st2 = e2e_step()
+        e2e_step_ms.append((time.perf_counter() - ts) * 1e3)
         if st2 is not None:
             e2e_rays += st2.extend_rays + st2.shadow_rays
     barrier()
@@ -433,7 +436,8 @@ def main():
             "samples_per_s": paths_total / (total_ms * 1e-3),
             "rays_per_step": rays_total / args.steps, "paths_per_step": paths_total / args.steps,
             "gpu_launches": launches_total,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "rank0_step_ms": [round(x, 2) for x in e2e_step_ms]},
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
