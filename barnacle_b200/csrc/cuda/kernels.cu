@@ -530,9 +530,11 @@ struct SceneArena {
 
 size_t wave_capacity_paths() {
   const char* e = std::getenv("BN_WAVE_PATHS");
-  // 16 Mi paths (3.3 GB of queues): launches of the deep bounces stay large enough that the
-  // drain at the end of each persistent kernel is a small share (measured 4 Mi -> 16 Mi: +12%)
-  size_t v = e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)16 << 20;
+  // 64 Mi paths (13 GB of queues on a 180 GB device): every launch of a wave, the deep bounces with
+  // few live paths above all, stays large enough that the drain at the end of each persistent kernel
+  // and the per-launch costs are a small share (measured on C2: 4 Mi -> 16 Mi +12%, 16 -> 64 Mi +5%,
+  // 128 Mi +0.6% more)
+  size_t v = e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)64 << 20;
   v = std::max<size_t>(v, 1024);
   return (v + 31) & ~(size_t)31;
 }

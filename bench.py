@@ -432,7 +432,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": label, "max_depth": MAX_DEPTH, "rr_depth": RR_DEPTH, "parallelism": f"sample-split x{world} + film reduce" if world > 1 else "single GPU",
-                       "l2_flush": "256 MiB memset between steps", "wave_paths": int(os.environ.get("BN_WAVE_PATHS", 16 << 20))},
+                       "l2_flush": "256 MiB memset between steps", "wave_paths": int(os.environ.get("BN_WAVE_PATHS", 64 << 20))},
             "samples_per_s": paths_total / (total_ms * 1e-3),
             "rays_per_step": rays_total / args.steps, "paths_per_step": paths_total / args.steps,
             "gpu_launches": launches_total,
