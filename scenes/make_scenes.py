@@ -16,6 +16,8 @@ GPU box — which has no /root/reference — can load them:
   scenes/material_sweep.json     C3: cbox room + pbr (metallic x roughness) and dielectric (ior) sweep, 1920x1080, 1024 spp
   scenes/bunny_instanced.json    C4: 64x64 bunny instances sharing one BLAS, 3840x2160, 512 spp
   scenes/cbox_mlt.json           C5 scene (pssmlt; a "next" row): C2 geometry, pssmlt integrator
+  scenes/cbox_ref.json           Asset/cbox.json as published (1024x768, thin lens, aces, pssmlt 16 spp) — the scene of the
+                                 reference's two sample PNGs; used by tests/test_ref_sample_image.py
 """
 import copy
 import json
@@ -186,6 +188,7 @@ def main():
     # 65 536 chains of 160 mutations: the chain count is the GPU's parallelism (reference default: 1024)
     c5["integrator"] = {"type": "pssmlt", "spp": 10, "max-depth": 8, "n-chains": 65536}
     dump("cbox_mlt.json", c5)
+    dump("cbox_ref.json", load_cbox())
     # small variants used by the parity tests (same geometry, tiny films)
     t = make_c4(n=8, width=128, height=72, spp=4)
     dump("bunny_instanced_small.json", t)
