@@ -6,8 +6,9 @@
 // atomic adds (the reference's Film.Accumulate is a racy read-modify-write).
 // Parallelism is therefore the chain count: the reference's default of 1024 chains leaves a
 // B200 mostly idle; scenes meant for the GPU should ask for >= 10^5 chains (`n-chains`).
-// Every ray goes through trace_exact (the op-for-op traversal), every transcendental through
-// include/bn_portable_math.h, so a chain evolves bit-identically to the oracle's.
+// Every ray goes through trace_lane (per-lane traversal, the op-for-op exact form; a fast-slab
+// variant exists behind BN_MLT_FAST_TRACE, bit-identical but slower here — see traverse.cuh), every
+// transcendental through include/bn_portable_math.h, so a chain evolves bit-identically to the oracle's.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -173,7 +174,7 @@ BN_DEV float3 mlt_li(const DScene& sc, float3 o, float3 d, MltCtx& ctx, unsigned
   int depth = 0;
   while (depth < p.max_depth) {
     TraceResult h;
-    trace_exact<false>(sc, o, d, CUDART_INF_F, h);
+    trace_lane<false>(sc, o, d, CUDART_INF_F, h);
     ++rays;
     if (!h.hit) break;
     const Surface sf = rebuild_surface(sc, o, d, h);
@@ -203,7 +204,7 @@ BN_DEV float3 mlt_li(const DScene& sc, float3 o, float3 d, MltCtx& ctx, unsigned
     const float3 wo_l = world_to_local(sf.onb, -d);
     if (ls.pdf != 0.f) {
       TraceResult sh;
-      trace_exact<true>(sc, sf.P, ls.wi, dist - 1e-3f, sh);
+      trace_lane<true>(sc, sf.P, ls.wi, dist - 1e-3f, sh);
       ++rays;
       if (!sh.hit) {
         const BsdfEval fe = material_eval(mat, wo_l, world_to_local(sf.onb, ls.wi));

@@ -46,14 +46,22 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef BN_REFILL_MIN
 #define BN_REFILL_MIN 12
 #endif
+#ifndef BN_REFILL_MIN_ANY
+#define BN_REFILL_MIN_ANY 16
+#endif
 constexpr int kRefillMin = BN_REFILL_MIN;  // refill when at least this many lanes are idle
+constexpr int kRefillMinAny = BN_REFILL_MIN_ANY;  // ... for any-hit (shadow) rays
 #ifndef BN_STAY_MIN
-#define BN_STAY_MIN 12
+#define BN_STAY_MIN 6
+#endif
+#ifndef BN_STAY_T
+#define BN_STAY_T 4
 #endif
 #ifndef BN_PREFETCH_AHEAD
 #define BN_PREFETCH_AHEAD 16384
 #endif
 constexpr int kPrefetchAhead = BN_PREFETCH_AHEAD;  // queue entries between a refill's loads and its L2 prefetches
+constexpr int kStayT = BN_STAY_T;        // same for phase T (33: one triangle per vote)
 constexpr int kStayMin = BN_STAY_MIN;      // phase N repeats without a vote while at least this many lanes are at a node (33: never)
 
 #ifdef BN_TRAV_STATS
@@ -116,8 +124,11 @@ struct TraceResult {
 // Exact per-lane traversal (slow path, fix-up kernel).  Same visiting order, the
 // reference's slab operations spelled out (slab<false>).
 // ---------------------------------------------------------------------------------
-template <bool ANY>
-BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, float t, TraceResult& res) {
+// FAST = true runs the same loop with the fast slab form (see slab<> in vecmath.cuh) and returns false
+// — result unusable — as soon as the ray turns out not to qualify in some object space; the caller
+// (trace_lane) then repeats it with FAST = false.  FAST = false always returns true.
+template <bool ANY, bool FAST>
+BN_DEV bool trace_lane_impl(const DScene& sc, const float3 wo, const float3 wd, float t, TraceResult& res) {
   uint2 stk[kStackSize];
   int sp = 0;
   const float3 winv = rcp3(wd);
@@ -126,16 +137,16 @@ BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, floa
   bool in_obj = false;
   int cur_inst = -1;
   res.hit = false; res.t = t; res.inst = -1; res.prim = -1; res.u = 0.f; res.v = 0.f;
-  if (!slab_pass<false>(slab<false>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv), t)) return;
+  if (!slab_pass<FAST>(slab<FAST>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv), t)) return true;
   uint32_t cur = sc.tlas.root | kTlasBit;
   for (;;) {
     if ((cur & kTlasBit) && in_obj) { o = wo; d = wd; inv = winv; signs = dir_signs(wd); in_obj = false; }
     if (!(cur & kLeafBit)) {
       const float4* np = reinterpret_cast<const float4*>(sc.nodes + (cur & kIndexMask));
       const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-      const Slab sl = slab<false>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
-      const Slab sr = slab<false>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
-      const bool pl = slab_pass<false>(sl, t), pr = slab_pass<false>(sr, t);
+      const Slab sl = slab<FAST>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
+      const Slab sr = slab<FAST>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
+      const bool pl = slab_pass<FAST>(sl, t), pr = slab_pass<FAST>(sr, t);
       const uint32_t level = cur & kTlasBit;
       const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
       const bool left_first = ((signs >> fbits(n3.z)) & 1u) != 0u;
@@ -158,14 +169,15 @@ BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, floa
         const int root = sphere_test(m2.z, oo, od, t, tp);
         if (root) {
           res.hit = true; res.inst = (int)slot; res.prim = root - 1; res.u = 0.f; res.v = 0.f;
-          if (ANY) return;
+          if (ANY) return true;
           t = tp; res.t = tp;
         }
       } else {
         o = oo; d = od; inv = rcp3(od); signs = dir_signs(od);
+        if (FAST && !slab_fast_ok(oo, inv)) return false;
         in_obj = true;
         cur_inst = (int)slot;
-        if (slab_pass<false>(slab<false>(f3(m0.x, m0.y, m0.z), f3(m1.x, m1.y, m1.z), o, inv), t)) { cur = fbits(m0.w); continue; }
+        if (slab_pass<FAST>(slab<FAST>(f3(m0.x, m0.y, m0.z), f3(m1.x, m1.y, m1.z), o, inv), t)) { cur = fbits(m0.w); continue; }
       }
     } else {
       const uint32_t count = (cur >> 27) & 7u, first = cur & kFirstMask;
@@ -173,23 +185,44 @@ BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, floa
         const float4* tp4 = reinterpret_cast<const float4*>(sc.tris + first + k);
         const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
         const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
-        const float3 lo = min_native(min_native(p0, p1), p2), hi = max_native(max_native(p0, p1), p2);
-        if (!slab_pass<false>(slab<false>(lo, hi, o, inv), t)) continue;
+        // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
+        const float3 lo = FAST ? f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z)) : min_native(min_native(p0, p1), p2);
+        const float3 hi = FAST ? f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z)) : max_native(max_native(p0, p1), p2);
+        if (!slab_pass<FAST>(slab<FAST>(lo, hi, o, inv), t)) continue;
         float tp, u, v;
         if (tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
           res.hit = true; res.inst = cur_inst; res.prim = (int)(first + k); res.u = u; res.v = v;
-          if (ANY) return;
+          if (ANY) return true;
           t = tp; res.t = tp;
         }
       }
     }
     for (;;) {
-      if (sp == 0) return;
+      if (sp == 0) return true;
       --sp;
       cur = stk[sp].x;
       if (ANY || __uint_as_float(stk[sp].y) <= t) break;
     }
   }
+}
+
+// The reference's operations one for one (fix-up kernel, bn_trace's exact mode).
+template <bool ANY>
+BN_DEV void trace_exact(const DScene& sc, const float3 wo, const float3 wd, float t, TraceResult& res) {
+  trace_lane_impl<ANY, false>(sc, wo, wd, t, res);
+}
+// Per-lane trace for callers that are not warp-synchronous (the PSSMLT megakernels).  With
+// BN_MLT_FAST_TRACE: the fast slab form whenever the ray qualifies (bit-identical — the PSSMLT parity
+// tests pass with it — same argument as for the persistent loop), else, or when some object space
+// disqualifies it half way, the exact form from scratch.  Measured on C5 and NOT the default: the
+// bootstrap kernel gains 9 % (35.9 -> 32.8 ms) but the chain kernel, which sits at its 128-register
+// cap with both forms inlined twice, loses 13 % (134 -> 152 ms).
+template <bool ANY>
+BN_DEV void trace_lane(const DScene& sc, const float3 wo, const float3 wd, float t, TraceResult& res) {
+#ifdef BN_MLT_FAST_TRACE
+  if (sc.all_finite != 0u && slab_fast_ok(wo, rcp3(wd)) && trace_lane_impl<ANY, true>(sc, wo, wd, t, res)) return;
+#endif
+  trace_lane_impl<ANY, false>(sc, wo, wd, t, res);
 }
 
 // ---------------------------------------------------------------------------------
@@ -281,7 +314,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
     const int n_idle = 32 - (nN + nT + nE + nS);
 
     // ---- refill idle lanes from the queue
-    if (n_idle != 0 && !exhausted && (n_idle >= kRefillMin || n_idle == 32)) {
+    if (n_idle != 0 && !exhausted && (n_idle >= (ANY ? kRefillMinAny : kRefillMin) || n_idle == 32)) {
       const unsigned idle = __ballot_sync(kFull, cur == kNone);
       int base = 0;
       if (lane == 0) base = atomicAdd(io.cursor(), n_idle);
@@ -361,27 +394,33 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
     } else if (nT >= nE && nT >= nS) {
       // ---- phase T: next triangle of the held BLAS leaf (slot order), behind its own
       // AABB test (Mesh.fs:229-233 — load-bearing)
-      BN_STAT(1, nT);
-      if (isT) {
-        const uint32_t count = (cur >> 27) & 7u;
-        const uint32_t tri = (cur & kFirstMask) + tri_k;
-        const float4* tp4 = tri_base + (size_t)tri * 3u;
-        const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
-        const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
-        // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
-        const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
-        const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
-        float tp, u, v;
-        bool done = false;
-        if (slab_pass<true>(slab<true>(lo, hi, o, inv), t) && tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
-          h_inst = cur_inst; h_prim = (int)tri; h_u = u; h_v = v;
-          if (ANY) { finish(); done = true; }
-          else t = tp;
+      // keep going while enough lanes still hold a triangle to test (same idea as phase N's repeat)
+      bool goT = isT;
+      for (;;) {
+        BN_STAT(1, __popc(__ballot_sync(kFull, goT)));
+        if (goT) {
+          const uint32_t count = (cur >> 27) & 7u;
+          const uint32_t tri = (cur & kFirstMask) + tri_k;
+          const float4* tp4 = tri_base + (size_t)tri * 3u;
+          const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
+          const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
+          // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
+          const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+          const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+          float tp, u, v;
+          bool done = false;
+          if (slab_pass<true>(slab<true>(lo, hi, o, inv), t) && tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
+            h_inst = cur_inst; h_prim = (int)tri; h_u = u; h_v = v;
+            if (ANY) { finish(); done = true; }
+            else t = tp;
+          }
+          if (!done) {
+            ++tri_k;
+            if (tri_k >= count) { tri_k = 0; pop(); }
+          }
+          goT = (cur >> 30) == 2u;
         }
-        if (!done) {
-          ++tri_k;
-          if (tri_k >= count) { tri_k = 0; pop(); }
-        }
+        if (__popc(__ballot_sync(kFull, goT)) < kStayT) break;
       }
     } else if (nE >= nS) {
       // ---- phase E: PrimitiveInstance.Intersect (Primitive.fs:111-129); the world AABB

@@ -12,8 +12,12 @@
 // pinned instead by (1) integer known-answer vectors derived from Util/Hash.fs,
 // (2) analytically known micro-scenes, (3) structural invariants of the BVH
 // builder, (4) an independent numpy restatement of the builder
-// (oracle/bvh_build_np.py).  Every "matches the reference" claim made with it
-// reads "matches the C++ restatement of the reference".
+// (oracle/bvh_build_np.py), and (5) — the one check against outputs of the F#
+// program itself — the reference's two published renders of Asset/cbox.json:
+// block means of the tone-mapped oracle film agree with them to 0.8 of 255
+// levels (tests/test_ref_sample_image.py; a statistical pin on 8-bit images, so
+// BIT-level parity stays unpinned).  Every "matches the reference" claim made
+// with it reads "matches the C++ restatement of the reference".
 //
 // Third-party arithmetic not under /root/reference: .NET 9 BCL
 // (System.Numerics.Vector3/Matrix4x4, MathF/Math), pinned only as `net9.0`
