@@ -327,8 +327,10 @@ struct BnHostScene {
 
 namespace {
 
-// Transform.Eval(t) (Base/Scene.fs:29-36); keyframe interpolation (animation)
-// is a "next" row and is rejected explicitly.
+// Transform.Eval(t) (Base/Scene.fs:26-36): the last keyframe at or before t; the first keyframe when
+// t precedes all of them; KeyFrame.Interpolate between it and the next one otherwise — also when t
+// sits exactly ON a keyframe that is not the last (ratio 0), which, with Transform.Compose as written
+// (host_math.hpp), is not that keyframe's matrix.  SURVEY §8(f) N4.
 M4 eval_transform(const NodeObj& n, float t) {
   if (n.key_matrix.empty()) return M4::identity();
   int prev = -1;
@@ -336,7 +338,7 @@ M4 eval_transform(const NodeObj& n, float t) {
     if (n.key_time[i] <= t) { prev = i; break; }
   if (prev < 0) return n.key_matrix[0];
   if (prev == (int)n.key_matrix.size() - 1) return n.key_matrix[prev];
-  throw std::runtime_error("keyframe interpolation (animated transforms) is out of scope of the hot path");
+  return interpolate_keyframes(n.key_time[prev], n.key_matrix[prev], n.key_time[prev + 1], n.key_matrix[prev + 1], t);
 }
 
 void traverse(const std::vector<NodeObj>& nodes, int idx, float t, const M4& parent, std::vector<InstanceObj>& objs,
