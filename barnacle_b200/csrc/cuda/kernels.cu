@@ -742,6 +742,14 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     BN_CUDA(cudaMemcpyAsync(h_counters.data(), s->counters, need * sizeof(int), cudaMemcpyDeviceToHost, stream));
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { s->poisoned = true; cuda_ok(e, "render waves"); return BN_ERR_CUDA; }
+    if (std::getenv("BN_DEBUG_COUNTS")) {  // debug aid: rays per launch (extend / shadow of every bounce of every wave), for the profiles
+      for (long long w = 0; w < n_waves; ++w) {
+        const int* base = h_counters.data() + per_wave * (size_t)w;
+        std::fprintf(stderr, "bn_counts wave %lld:", w);
+        for (int b = 0; b < D; ++b) std::fprintf(stderr, " b%d extend=%d shadow=%d", b, base[(size_t)b * CS], base[(size_t)(D + 1 + b) * CS]);
+        std::fprintf(stderr, "\n");
+      }
+    }
     if (stats) {
       uint64_t ext = 0, sh = 0;
       for (long long w = 0; w < n_waves; ++w) {

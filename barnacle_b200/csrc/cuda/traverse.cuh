@@ -44,7 +44,7 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;  // lane idle (a leaf ref that no scene 
 constexpr uint32_t kScan = 0xFFFFFFFEu;  // lane is at the small-TLAS ordered scan (ditto)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef BN_REFILL_MIN
-#define BN_REFILL_MIN 12
+#define BN_REFILL_MIN 14
 #endif
 #ifndef BN_REFILL_MIN_ANY
 #define BN_REFILL_MIN_ANY 16

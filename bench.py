@@ -397,10 +397,16 @@ def main():
         achieved = tot["extend"] * b_ext / ext_s / 1e9 if ext_s > 0 else None
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and args.workload == "C2":
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         n_ext_launches = max(1, tot["launches"] // (2 + 5 * MAX_DEPTH) * MAX_DEPTH)   # launches per wave = 2 + 5*maxDepth, maxDepth of them are extends
+        if os.path.exists(tpath) and args.workload == "C2":
+            # ncu's DRAM bytes of ONE profiled extend launch, per ray of that launch, times the rays of this run's average
+            # launch: "per launch like achieved"
+            tj = json.load(open(tpath))
+            if tj.get("dram_bytes_per_ray"):
+                traffic = tj["dram_bytes_per_ray"] * tot["extend"] / n_ext_launches
+                traffic_src = tj["source"] + f"; {tj['dram_bytes_per_ray']:.1f} DRAM B/ray of the profiled launch x the rays of this run's average extend launch"
+            else:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         roofline = {"bound": "hbm", "kernel": "k_traverse<closest> (extend: TLAS+BLAS closest-hit traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": tot["extend"] * b_ext / n_ext_launches, "avg_launch_ms": tot["extend_ms"] / n_ext_launches,
