@@ -75,3 +75,59 @@ def test_scene_load_ex_with_host_builder_equals_scene_load(lib, root):
     assert ctypes.string_at(da.tlas_nodes, da.tlas_node_count * 32) == ctypes.string_at(db.tlas_nodes, db.tlas_node_count * 32)
     assert ctypes.string_at(da.instances, da.instance_count * 168) == ctypes.string_at(db.instances, db.instance_count * 168)
     b.close()
+
+
+# ---- the F# binding delivered as source (integration/fsharp/GpuIntegrators.fs) ----------------------------
+# It cannot be compiled here (no dotnet), so its struct mirrors are pinned field by field against the ctypes
+# mirror above, which test_struct_sizes / the GPU tests pin against the header and the library.
+_FS_TYPES = {"uint32": (4, 4), "int": (4, 4), "float32": (4, 4), "float": (8, 8), "uint64": (8, 8), "nativeint": (8, 8),
+             "Vector3": (12, 4), "Matrix4x4": (64, 4)}
+
+
+def _fsharp_structs(root):
+    text = open(os.path.join(root, "integration", "fsharp", "GpuIntegrators.fs")).read()
+    out = {}
+    for m in re.finditer(r"type (Bn\w+) = // (\d+)[^\n]*\n((?:\s+val mutable \w+: \w+[^\n]*\n)+)", text):
+        fields = re.findall(r"val mutable (\w+): (\w+)", m.group(3))
+        out[m.group(1)] = (int(m.group(2)), fields)
+    return out
+
+
+def _sequential_layout(fields, known):
+    """.NET LayoutKind.Sequential == the C rule: natural alignment per field, size rounded to the largest."""
+    off, align, offsets = 0, 1, []
+    for _, ty in fields:
+        size, a = known[ty]
+        off = (off + a - 1) // a * a
+        offsets.append(off)
+        off += size
+        align = max(align, a)
+    return offsets, (off + align - 1) // align * align, align
+
+
+def test_fsharp_binding_structs_match_the_c_abi(root):
+    structs = _fsharp_structs(root)
+    mirror = {"BnInstance": _ffi.BnInstance, "BnMesh": _ffi.BnMesh, "BnMaterial": _ffi.BnMaterial, "BnLight": _ffi.BnLight,
+              "BnCamera": _ffi.BnCamera, "BnSceneDesc": _ffi.BnSceneDesc, "BnRenderParams": _ffi.BnRenderParams,
+              "BnStats": _ffi.BnStats, "BnMltParams": _ffi.BnMltParams, "BnMltStats": _ffi.BnMltStats}
+    assert sorted(structs) == sorted(mirror)
+    known = dict(_FS_TYPES)
+    for name in ["BnInstance", "BnMesh", "BnMaterial", "BnLight", "BnCamera", "BnSceneDesc", "BnRenderParams", "BnStats",
+                 "BnMltParams", "BnMltStats"]:
+        quoted, fields = structs[name]
+        offsets, size, align = _sequential_layout(fields, known)
+        known[name] = (size, align)
+        ct = mirror[name]
+        assert size == quoted == ctypes.sizeof(ct), name
+        assert len(fields) == len(ct._fields_), name
+        for (fs_name, _), off, (c_name, _) in zip(fields, offsets, ct._fields_):
+            assert off == getattr(ct, c_name).offset, f"{name}.{fs_name} vs {c_name}"
+            # same field, modulo naming convention (camelCase vs snake_case; `kind` is `type`, a keyword in F#)
+            assert fs_name.lower() == c_name.replace("_", "") or (fs_name, c_name) == ("kind", "type"), f"{name}.{fs_name} vs {c_name}"
+
+
+def test_fsharp_binding_imports_only_declared_symbols(root):
+    text = open(os.path.join(root, "integration", "fsharp", "GpuIntegrators.fs")).read()
+    imported = set(re.findall(r"extern \w+ (bn_\w+)\(", text))
+    assert imported and imported <= set(_ffi.SYMBOLS)
+    assert {"bn_scene_create", "bn_scene_destroy", "bn_render", "bn_render_pssmlt", "bn_last_error"} <= imported
