@@ -237,9 +237,23 @@ BN_DEV void trace_lane(const DScene& sc, const float3 wo, const float3 wd, float
 // ray touches a few times in its life (committed hit, queue slot, world direction, candidate mask)
 // lives there instead of in registers; that is what lets the kernel fit 9 CTAs per SM.
 constexpr int kTravColdWords = 9;
+// Traversal stack entry.  Closest hit: (ref, entry distance), re-checked against the current t at pop.
+// Any hit: t is fixed, the entry distance is never read again, so shadow rays keep refs only (half the
+// local-memory traffic of their pushes and pops).
+template <bool ANY> struct TravStack;
+template <> struct TravStack<false> {
+  using type = uint2;
+  static BN_DEV void push(uint2& e, uint32_t ref, float tmin) { e = make_uint2(ref, __float_as_uint(tmin)); }
+  static BN_DEV bool pop(const uint2& e, float t, uint32_t& cur) { if (__uint_as_float(e.y) <= t) { cur = e.x; return true; } return false; }
+};
+template <> struct TravStack<true> {
+  using type = uint32_t;
+  static BN_DEV void push(uint32_t& e, uint32_t ref, float) { e = ref; }
+  static BN_DEV bool pop(const uint32_t& e, float, uint32_t& cur) { cur = e; return true; }
+};
 template <bool ANY, class IO>
 BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__ cold, const int cold_stride) {
-  uint2 stk[kStackSize];  // (ref, entry distance bits)
+  typename TravStack<ANY>::type stk[kStackSize];
   // per-lane state
   float3 wo, winv;        // world-space ray (origin, 1/direction)
   float3 o, d, inv;       // ray in the CURRENT space
@@ -293,8 +307,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
         return;
       }
       --sp;
-      const uint2 e = stk[sp];
-      if (ANY || __uint_as_float(e.y) <= t) { cur = e.x; break; }
+      if (TravStack<ANY>::pop(stk[sp], t, cur)) break;
     }
     if ((cur & kTlasBit) && in_obj) {  // tree TLAS: back from a BLAS, restore the world-space ray (d is only read inside a BLAS)
       o = wo; inv = winv;
@@ -365,11 +378,12 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
 
     if (nN >= nT && nN >= nE && nN >= nS) {
       // ---- phase N: one node step (64-B GNode, two slab tests)
-      // keep stepping while enough lanes still have a node step to do (one ballot instead of a vote)
-      bool goN = isN;
+      // keep stepping while enough lanes still have a node step to do (one ballot instead of a vote).
+      // "This lane is at a node" is read off `cur` (sign bit = kLeafBit) each time: a loop-carried flag
+      // costs five instructions per step to keep in a register.
       for (;;) {
-        BN_STAT(0, __popc(__ballot_sync(kFull, goN)));
-        if (goN) {
+        BN_STAT(0, __popc(__ballot_sync(kFull, (int)cur >= 0)));
+        if ((int)cur >= 0) {
           const float4* np = node_base + (size_t)(cur & kIndexMask) * 4u;
           const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
           const Slab sl = slab<true>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
@@ -378,27 +392,26 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
           const uint32_t level = cur & kTlasBit;
           const bool lf = ((signs >> fbits(n3.z)) & 1u) != 0u;  // left first iff dir[splitAxis] > 0 (BVH.fs:51-56 / Mesh.fs:235-240)
           const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
-          if (pl & pr) {
-            cur = lf ? left : right;
-            stk[sp] = make_uint2(lf ? right : left, __float_as_uint(lf ? sr.tmin : sl.tmin));
-            ++sp;
-          } else if (pl | pr) {
-            cur = pl ? left : right;
+          if (!pl) {  // branches on the two predicates as they are (no pl | pr to materialise)
+            if (pr) cur = right;
+            else pop();
+          } else if (!pr) {
+            cur = left;
           } else {
-            pop();
+            cur = lf ? left : right;
+            TravStack<ANY>::push(stk[sp], lf ? right : left, lf ? sr.tmin : sl.tmin);
+            ++sp;
           }
-          goN = !(cur & kLeafBit);
         }
-        if (__popc(__ballot_sync(kFull, goN)) < kStayMin) break;
+        if (__popc(__ballot_sync(kFull, (int)cur >= 0)) < kStayMin) break;
       }
     } else if (nT >= nE && nT >= nS) {
       // ---- phase T: next triangle of the held BLAS leaf (slot order), behind its own
       // AABB test (Mesh.fs:229-233 — load-bearing)
       // keep going while enough lanes still hold a triangle to test (same idea as phase N's repeat)
-      bool goT = isT;
       for (;;) {
-        BN_STAT(1, __popc(__ballot_sync(kFull, goT)));
-        if (goT) {
+        BN_STAT(1, __popc(__ballot_sync(kFull, (cur >> 30) == 2u)));
+        if ((cur >> 30) == 2u) {
           const uint32_t count = (cur >> 27) & 7u;
           const uint32_t tri = (cur & kFirstMask) + tri_k;
           const float4* tp4 = tri_base + (size_t)tri * 3u;
@@ -418,9 +431,8 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
             ++tri_k;
             if (tri_k >= count) { tri_k = 0; pop(); }
           }
-          goT = (cur >> 30) == 2u;
         }
-        if (__popc(__ballot_sync(kFull, goT)) < kStayT) break;
+        if (__popc(__ballot_sync(kFull, (cur >> 30) == 2u)) < kStayT) break;
       }
     } else if (nE >= nS) {
       // ---- phase E: PrimitiveInstance.Intersect (Primitive.fs:111-129); the world AABB
