@@ -1,0 +1,127 @@
+"""Pins the oracle's TLAS + BLAS traversal against geometry, without any BVH.
+
+The reference has no tests, so the oracle (oracle/barnacle_oracle.cpp) is what every GPU parity
+test compares with.  Its traversal — the flattened scene, both BVH builds, the front-to-back walk, instance
+transforms, triangle and sphere tests — is cross-checked here against a float64 brute force over EVERY
+primitive of the scene (numpy, written independently: plain Moller-Trumbore / quadratic roots on world-space
+primitives).  The two can differ only where float32 rounding decides (grazing rays, edges shared by two
+triangles, SURVEY Q13's per-triangle boxes), so agreement is required on >= 99.8 % of the rays and to 1e-4
+relative in t;
+a wrong tree, a mis-ordered walk, a wrong permutation or transform would fail it by far.
+"""
+import numpy as np
+import pytest
+
+from conftest import random_rays
+from oracle.oracle_ffi import OracleScene
+
+
+def _world_primitives(desc):
+    """Per mesh instance (index, world-space triangles [n,3,3] float64) and per sphere instance (index, world->object, radius)."""
+    verts = np.ctypeslib.as_array(desc.vertices, shape=(desc.vertex_count, 3)).astype(np.float64)
+    idx = np.ctypeslib.as_array(desc.triangles, shape=(desc.triangle_count, 3))
+    meshes, spheres = [], []
+    for i in range(desc.instance_count):
+        inst = desc.instances[i]
+        o2w = np.array(inst.object_to_world[:], dtype=np.float64).reshape(4, 4)  # row-vector convention: p' = p . M
+        if inst.prim_kind == 0:
+            m = desc.meshes[inst.prim_id]
+            v = verts[m.vertex_offset:m.vertex_offset + m.vertex_count]
+            vw = v @ o2w[:3, :3] + o2w[3, :3]
+            meshes.append((i, vw[idx[m.tri_offset:m.tri_offset + m.tri_count]]))
+        else:
+            w2o = np.array(inst.world_to_object[:], dtype=np.float64).reshape(4, 4)
+            spheres.append((i, w2o, float(desc.sphere_radii[inst.prim_id])))
+    return meshes, spheres
+
+
+def _rays_through_box(o, d, lo, hi):
+    """Rays whose line can meet the (padded) box at t > 0: the only culling used, so that the many-instance scene
+    stays affordable.  It is geometry (a triangle inside the box cannot be hit by a ray that misses the box), not a BVH."""
+    pad = 1e-6 * (1.0 + np.abs(hi - lo).max())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t0, t1 = (lo - pad - o) / d, (hi + pad - o) / d
+    near = np.nanmax(np.minimum(t0, t1), axis=1)
+    far = np.nanmin(np.maximum(t0, t1), axis=1)
+    return (near <= far) & (far > 0)
+
+
+def _brute_force_closest(desc, rays, chunk=32):
+    meshes, spheres = _world_primitives(desc)
+    o = rays["origin"].astype(np.float64)
+    d = rays["direction"].astype(np.float64)
+    n = o.shape[0]
+    best_t = np.full(n, np.inf)
+    best_i = np.full(n, -1, dtype=np.int64)
+    for inst, tris in meshes:
+        cand = np.flatnonzero(_rays_through_box(o, d, tris.min(axis=(0, 1)), tris.max(axis=(0, 1))))
+        # component arrays [rays of the chunk, triangles]: an order of magnitude faster than np.cross / einsum on broadcasts
+        p0x, p0y, p0z = (tris[:, 0, k][None] for k in range(3))
+        e0x, e0y, e0z = ((tris[:, 1, k] - tris[:, 0, k])[None] for k in range(3))
+        e1x, e1y, e1z = ((tris[:, 2, k] - tris[:, 0, k])[None] for k in range(3))
+        for a in range(0, cand.size, chunk):
+            r = cand[a:a + chunk]
+            ox, oy, oz = (o[r, k, None] for k in range(3))
+            dx, dy, dz = (d[r, k, None] for k in range(3))
+            px, py, pz = dy * e1z - dz * e1y, dz * e1x - dx * e1z, dx * e1y - dy * e1x  # d x e1
+            det = e0x * px + e0y * py + e0z * pz
+            sx, sy, sz = ox - p0x, oy - p0y, oz - p0z
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = 1.0 / det
+                u = (sx * px + sy * py + sz * pz) * inv
+                qx, qy, qz = sy * e0z - sz * e0y, sz * e0x - sx * e0z, sx * e0y - sy * e0x  # s x e0
+                v = (dx * qx + dy * qy + dz * qz) * inv
+                t = (e1x * qx + e1y * qy + e1z * qz) * inv
+            ok = (det != 0) & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > 0)
+            tk = np.where(ok, t, np.inf).min(axis=1)
+            better = tk < best_t[r]
+            best_t[r] = np.where(better, tk, best_t[r])
+            best_i[r] = np.where(better, inst, best_i[r])
+    for i, w2o, radius in spheres:
+        oo = o @ w2o[:3, :3] + w2o[3, :3]
+        dd = d @ w2o[:3, :3]  # directions: no translation; NOT renormalised, so t is shared with world space
+        A = np.einsum("rk,rk->r", dd, dd)
+        B = 2 * np.einsum("rk,rk->r", oo, dd)
+        Cq = np.einsum("rk,rk->r", oo, oo) - radius * radius
+        disc = B * B - 4 * A * Cq
+        with np.errstate(invalid="ignore"):
+            sq = np.sqrt(np.where(disc >= 0, disc, np.nan))
+            t0, t1 = (-B - sq) / (2 * A), (-B + sq) / (2 * A)
+        eps = 1e-3  # SpherePrimitive.Intersect's own epsilon (Sphere.fs:14)
+        ts = np.where(t0 > eps, t0, np.where(t1 > eps, t1, np.inf))
+        ts = np.where(np.isnan(ts), np.inf, ts)
+        better = ts < best_t
+        best_t = np.where(better, ts, best_t)
+        best_i = np.where(better, i, best_i)
+    return best_t, best_i
+
+
+@pytest.mark.parametrize("name,n_rays", [("cbox_pt", 4096), ("material_sweep", 4096), ("bunny_instanced_small", 2048), ("cbox_bunny", 2048)])
+def test_oracle_traversal_agrees_with_brute_force(scene_loader, name, n_rays):
+    scene = scene_loader(name)
+    desc = scene.desc.contents
+    rays = random_rays(scene, n_rays, seed=20260 + n_rays)
+    oracle = OracleScene(scene.desc)
+    hits = oracle.trace(rays)
+    bt, bi = _brute_force_closest(desc, rays)
+
+    o_hit, b_hit = hits["instance"] >= 0, np.isfinite(bt)
+    # origins inside a wall / on a surface give sub-epsilon brute-force hits the reference's boxes (tMin = 1e-3) skip
+    clear = ~b_hit | (bt > 1e-2)
+    same_status = (o_hit == b_hit) | ~clear
+    both = o_hit & b_hit & clear
+    close = np.abs(hits["t"][both].astype(np.float64) - bt[both]) <= 1e-4 * np.maximum(1.0, bt[both])
+    same_inst = hits["instance"][both] == bi[both]
+    assert b_hit.mean() > 0.5, "degenerate batch"
+    tol = max(0.002, 1.5 / n_rays)  # at most 0.2 % of the rays (one ray in the small batches) may sit on a rounding boundary
+    assert (~same_status).mean() <= tol, f"hit/miss differs on {(~same_status).sum()} of {n_rays} rays"
+    assert (~close).mean() <= tol, f"t differs on {(~close).sum()} of {both.sum()} hits"
+    assert (~same_inst & close).mean() <= tol, f"instance differs on {(~same_inst & close).sum()} hits with equal t"
+
+    # any-hit (PrimitiveAggregate.Intersect/2): occluded iff something lies before tmax
+    sel = np.flatnonzero(both)[close]
+    short, long_ = rays[sel].copy(), rays[sel].copy()
+    short["tmax"] = (bt[sel] * 0.9).astype(np.float32)
+    long_["tmax"] = (bt[sel] * 1.1 + 1e-2).astype(np.float32)
+    assert (oracle.trace(short, any_hit=True)["instance"] != 0).mean() <= tol
+    assert (oracle.trace(long_, any_hit=True)["instance"] != 1).mean() <= tol
