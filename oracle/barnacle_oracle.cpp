@@ -1040,6 +1040,19 @@ BO_API float bo_lcg(uint32_t* state) { return lcg(*state); }
 BO_API void bo_sincos(float x, float* s, float* c) { o_sincos(x, *s, *c); }
 BO_API float bo_atan(float x) { return o_atan(x); }
 
+// Material entry points for function-level tests (tests/test_oracle_materials.py checks them against an
+// independent float64 restatement of Lambertian.fs / Mirror.fs / Dielectric.fs / PBR.fs).
+// out_eval: bsdf.xyz, pdf.   out_sample: bsdf.xyz, pdf, wi.xyz.
+BO_API void bo_material_eval(const BnMaterial* m, const float* wo, const float* wi, float* out_eval) {
+  const BSDFEval e = material_eval(*m, V3{wo[0], wo[1], wo[2]}, V3{wi[0], wi[1], wi[2]});
+  out_eval[0] = e.bsdf.x; out_eval[1] = e.bsdf.y; out_eval[2] = e.bsdf.z; out_eval[3] = e.pdf;
+}
+BO_API void bo_material_sample(const BnMaterial* m, const float* wo, float ulobe, const float* u, float* out_sample) {
+  const BSDFSample b = material_sample(*m, V3{wo[0], wo[1], wo[2]}, ulobe, V2{u[0], u[1]});
+  out_sample[0] = b.eval.bsdf.x; out_sample[1] = b.eval.bsdf.y; out_sample[2] = b.eval.bsdf.z; out_sample[3] = b.eval.pdf;
+  out_sample[4] = b.wi.x; out_sample[5] = b.wi.y; out_sample[6] = b.wi.z;
+}
+
 BO_API int bo_scene_create(const BnSceneDesc* d, BoScene** out) {
   if (!d || !out) return -1;
   auto* b = new BoScene();
@@ -1060,6 +1073,16 @@ BO_API int bo_scene_create(const BnSceneDesc* d, BoScene** out) {
   return 0;
 }
 BO_API void bo_scene_destroy(BoScene* s) { delete s; }
+
+// UniformLightSampler.Sample for function-level tests (tests/test_oracle_lights.py).
+// out: eval.p.xyz, eval.L.xyz, eval.pdf, wi.xyz
+BO_API void bo_light_sample(const BoScene* sc, const float* p, float usel, const float* ul, float* out) {
+  const LightSample ls = light_sampler_sample(sc->s, V3{p[0], p[1], p[2]}, usel, V2{ul[0], ul[1]});
+  out[0] = ls.eval.p.x; out[1] = ls.eval.p.y; out[2] = ls.eval.p.z;
+  out[3] = ls.eval.L.x; out[4] = ls.eval.L.y; out[5] = ls.eval.L.z;
+  out[6] = ls.eval.pdf;
+  out[7] = ls.wi.x; out[8] = ls.wi.y; out[9] = ls.wi.z;
+}
 
 // counters: [tlas_nodes, blas_nodes, tris_fetched, tris_box_pass, inst_visited, inst_box_pass, inst_committed, rays]
 static void export_counters(const Counters& c, uint64_t* out) {

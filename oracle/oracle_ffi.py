@@ -52,6 +52,9 @@ def load() -> C.CDLL:
         lib.bo_render_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_set_portable_math.argtypes = [C.c_int]
+        lib.bo_light_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        lib.bo_material_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.bo_material_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         lib.bo_pssmlt_bootstrap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_render_pssmlt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = lib
@@ -91,6 +94,12 @@ class OracleScene:
         out = np.zeros(12, dtype=np.float32)
         hit = self._lib.bo_closest_geom(self._h, ray.ctypes.data, out.ctypes.data)
         return bool(hit), out.reshape(4, 3)
+
+    def light_sample(self, p, usel: float, ulight) -> np.ndarray:
+        """UniformLightSampler.Sample(p, uSelect, uLight): (eval.p xyz, eval.L xyz, eval.pdf, wi xyz)."""
+        p, ul, out = np.asarray(p, np.float32), np.asarray(ulight, np.float32), np.zeros(10, np.float32)
+        self._lib.bo_light_sample(self._h, p.ctypes.data, float(usel), ul.ctypes.data, out.ctypes.data)
+        return out
 
     def primary_rays(self, params) -> np.ndarray:
         n = (params.sample_end - params.sample_begin) * (params.y1 - params.y0) * (params.x1 - params.x0)
@@ -137,6 +146,20 @@ class OracleScene:
             stats["extend_counters"] = dict(zip(COUNTER_NAMES, (int(x) for x in ce)))
             stats["shadow_counters"] = dict(zip(COUNTER_NAMES, (int(x) for x in cs)))
         return film, stats
+
+
+def material_eval(material, wo, wi) -> np.ndarray:
+    """(bsdf.xyz, pdf) of MaterialBase.Eval for a BnMaterial (ctypes struct of the product binding)."""
+    wo, wi, out = np.asarray(wo, np.float32), np.asarray(wi, np.float32), np.zeros(4, np.float32)
+    load().bo_material_eval(C.addressof(material), wo.ctypes.data, wi.ctypes.data, out.ctypes.data)
+    return out
+
+
+def material_sample(material, wo, ulobe: float, u) -> np.ndarray:
+    """(bsdf.xyz, pdf, wi.xyz) of MaterialBase.Sample."""
+    wo, u, out = np.asarray(wo, np.float32), np.asarray(u, np.float32), np.zeros(7, np.float32)
+    load().bo_material_sample(C.addressof(material), wo.ctypes.data, float(ulobe), u.ctypes.data, out.ctypes.data)
+    return out
 
 
 def set_portable_math(on: bool) -> None:
