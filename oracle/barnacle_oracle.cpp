@@ -1123,6 +1123,20 @@ BO_API int bo_trace(const BoScene* sc, const BnRay* rays, uint64_t n, int any_hi
   return 0;
 }
 
+// UniformLightSampler.Eval at the closest hit of `ray` (tests/test_oracle_li.py): out = L.xyz, pdf.
+// Returns 0 when the ray hits nothing or something that is not an emitter.
+BO_API int bo_light_eval_hit(const BoScene* sc, const BnRay* ray, float* out) {
+  Interaction it{};
+  float t = ray->tmax;
+  Counters c;
+  Ray r{load3(ray->origin), load3(ray->direction)};
+  if (!scene_closest<false>(sc->s, r, it, t, &c)) return 0;
+  if (sc->s.inst[it.inst].light_id < 0) return 0;
+  const LightEval le = light_sampler_eval(sc->s, r.o, it);
+  out[0] = le.L.x; out[1] = le.L.y; out[2] = le.L.z; out[3] = le.pdf;
+  return 1;
+}
+
 // World-space interaction of a closest hit (for shading parity / debugging):
 // out = p[3], n[3], t[3], b[3]
 BO_API int bo_closest_geom(const BoScene* sc, const BnRay* ray, float* out) {

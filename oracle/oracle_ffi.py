@@ -52,6 +52,7 @@ def load() -> C.CDLL:
         lib.bo_render_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_set_portable_math.argtypes = [C.c_int]
+        lib.bo_light_eval_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.bo_light_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         lib.bo_material_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.bo_material_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
@@ -94,6 +95,12 @@ class OracleScene:
         out = np.zeros(12, dtype=np.float32)
         hit = self._lib.bo_closest_geom(self._h, ray.ctypes.data, out.ctypes.data)
         return bool(hit), out.reshape(4, 3)
+
+    def light_eval_hit(self, ray: np.ndarray):
+        """UniformLightSampler.Eval(ray.Origin, interaction) at the closest hit: (L xyz, pdf), or None if not an emitter."""
+        ray = np.ascontiguousarray(ray, dtype=RAY_DTYPE)
+        out = np.zeros(4, dtype=np.float32)
+        return out if self._lib.bo_light_eval_hit(self._h, ray.ctypes.data, out.ctypes.data) else None
 
     def light_sample(self, p, usel: float, ulight) -> np.ndarray:
         """UniformLightSampler.Sample(p, uSelect, uLight): (eval.p xyz, eval.L xyz, eval.pdf, wi xyz)."""
