@@ -103,3 +103,78 @@ def test_li_control_flow_matches_restatement(scene_loader, oracle_lib, name, max
     assert lit > 0.5 * n, "degenerate test: most paths carry no radiance"
     assert bad == 0, f"{bad} of {n} paths differ from the oracle's Li"
     assert exact >= 0.98 * n, f"only {exact} of {n} paths are bit-identical (measured: all of them)"
+
+
+# ---- the two other ProgressiveIntegrators ("next" row N4) ------------------------------------------------------
+
+def _hit(oracle, desc, o, d):
+    ray = _ray(o, d, np.inf)
+    hit = oracle.trace(ray)[0]
+    if hit["instance"] < 0:
+        return None
+    _, g = oracle.closest_geom(ray)
+    return ray, desc.instances[int(hit["instance"])], tuple(g[k].astype(F) for k in range(4))
+
+
+def restated_direct_li(oracle, desc, o, d, sampler):  # Direct.fs:10-40
+    L = np.zeros(3, F)
+    h = _hit(oracle, desc, o, d)
+    if h is None:
+        return L
+    _, inst, (p, n, t, b) = h
+    to_local = lambda v: np.array([_dot(v, t), _dot(v, b), _dot(v, n)], F)
+    to_world = lambda v: (F(v[0]) * t + F(v[1]) * b) + F(v[2]) * n
+    if inst.light_id >= 0:                                              # :16-17, DiffuseLight.Eval (Light.fs:49-53)
+        light = desc.lights[inst.light_id]
+        woz = to_local(-d)[2]
+        if abs(woz) > F(1e-6) and (woz > 0 or light.two_sided):
+            L = L + np.array(light.emission[:], F)
+    if inst.material_id < 0:
+        return L
+    mat = desc.materials[inst.material_id]
+    ls = oracle.light_sample(p, sampler.next1d(), sampler.next2d())     # :20-21
+    diff = ls[0:3] - p
+    dist = F(np.sqrt(_dot(diff, diff)))
+    wo_local = to_local(-d)
+    if oracle.trace(_ray(p, ls[7:10], F(dist - F(1e-3))), any_hit=True)[0]["instance"] == 0:   # traced whatever the pdf (:25)
+        e = oracle_ffi.material_eval(mat, wo_local, to_local(ls[7:10]))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            L = _fma3(e[:3], ls[3:6] * F(F(1) / ls[6]), L)              # no MIS, a true division (:28-29)
+    bs = oracle_ffi.material_sample(mat, wo_local, sampler.next1d(), sampler.next2d())          # :31
+    h2 = _hit(oracle, desc, p, to_world(bs[4:7]))                       # followed whatever its pdf (:32-36)
+    if h2 is not None and h2[1].light_id >= 0:
+        le = oracle.light_eval_hit(h2[0])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            L = _fma3(bs[:3], le[:3] * F(F(1) / le[3]), L)              # weighted by 1 / pdf_light (sic, :37-38)
+    return L
+
+
+@pytest.mark.parametrize("name", ["cbox_pt", "material_sweep"])
+def test_direct_and_normal_integrators_match_restatement(scene_loader, oracle_lib, name):
+    from barnacle_b200 import _ffi
+    oracle_ffi.set_portable_math(False)
+    scene = scene_loader(name)
+    desc = scene.desc.contents
+    oracle = OracleScene(scene.desc)
+    w, h, spp = 20, 14, 2
+    rays = oracle.primary_rays(make_params(w, h, spp)).reshape(spp, h, w)
+    direct = oracle.render_radiance(make_params(w, h, spp, integrator=_ffi.BN_INTEGRATOR_DIRECT), threads=1)
+    normal = oracle.render_radiance(make_params(w, h, spp, integrator=_ffi.BN_INTEGRATOR_NORMAL), threads=1)
+    n = exact = lit = 0
+    for s in range(spp):
+        for y in range(h):
+            for x in range(w):
+                r = rays[s, y, x]
+                o, d = r["origin"].astype(F), r["direction"].astype(F)
+                hit = _hit(oracle, desc, o, d)
+                want_n = np.zeros(3, F) if hit is None else F(0.5) * (hit[2][1] + F(1))      # Normal.fs:14-17
+                np.testing.assert_array_equal(normal[s, y, x], want_n)
+                sampler = PySampler(x, y, s)
+                sampler.next2d(), sampler.next2d()
+                got = restated_direct_li(oracle, desc, o, d, sampler)
+                ref = direct[s, y, x]
+                assert np.allclose(got, ref, rtol=1e-4, atol=1e-6, equal_nan=True), (x, y, s, got, ref)
+                n += 1
+                exact += np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+                lit += bool(np.nan_to_num(ref).any())
+    assert lit > 0.5 * n and exact >= 0.98 * n, (lit, exact, n)
