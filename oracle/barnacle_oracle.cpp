@@ -1255,6 +1255,26 @@ BO_API int bo_render(const BoScene* sc, const BnRenderParams* p, float* film, ui
   return 0;
 }
 
+// MLTSampler driven by a script (tests/test_oracle_mlt_sampler.py): ops 0 = StartIteration, 1 = Next1D (its value is
+// appended to `out`), 2 = Accept, 3 = Reject.  Returns the number of values written.
+BO_API int bo_mlt_sampler_script(uint32_t seed_state, float large_step_prob, int strategy, float p0, float p1, const int32_t* script, int n,
+                                 int n_dims, float* out) {
+  std::vector<PrimarySample> xs((size_t)n_dims);
+  BnMltParams p{};
+  p.large_step_prob = large_step_prob; p.strategy = strategy; p.p0 = p0; p.p1 = p1;
+  MltSampler m = make_mlt_sampler(p, seed_state, xs.data());
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    switch (script[i]) {
+      case 0: m.start_iteration(); break;
+      case 1: if (m.sample_index >= n_dims) return -1; out[k++] = m.next1d(); break;
+      case 2: m.accept(); break;
+      default: m.reject(); break;
+    }
+  }
+  return k;
+}
+
 // PSSMLTIntegrator.Render phase 1 — PSSMLT.fs:382-392: BootstrapWeights[n_bootstrap]
 BO_API int bo_pssmlt_bootstrap(const BoScene* sc, const BnMltParams* p, float* weights, uint64_t* rays, int threads) {
   const Scene& s = sc->s;

@@ -52,6 +52,7 @@ def load() -> C.CDLL:
         lib.bo_render_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_set_portable_math.argtypes = [C.c_int]
+        lib.bo_mlt_sampler_script.argtypes = [C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.bo_light_eval_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.bo_light_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         lib.bo_material_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -166,6 +167,15 @@ def material_sample(material, wo, ulobe: float, u) -> np.ndarray:
     """(bsdf.xyz, pdf, wi.xyz) of MaterialBase.Sample."""
     wo, u, out = np.asarray(wo, np.float32), np.asarray(u, np.float32), np.zeros(7, np.float32)
     load().bo_material_sample(C.addressof(material), wo.ctypes.data, float(ulobe), u.ctypes.data, out.ctypes.data)
+    return out
+
+
+def mlt_sampler_script(seed_state: int, large_step_prob: float, strategy: int, p0: float, p1: float, script, n_dims: int) -> np.ndarray:
+    """Runs MLTSampler (PSSMLT.fs:35-150) through a script of ops (0 StartIteration, 1 Next1D, 2 Accept, 3 Reject); returns the draws."""
+    script = np.ascontiguousarray(script, dtype=np.int32)
+    out = np.zeros(int((script == 1).sum()), dtype=np.float32)
+    k = load().bo_mlt_sampler_script(seed_state, large_step_prob, strategy, p0, p1, script.ctypes.data, len(script), n_dims, out.ctypes.data)
+    assert k == len(out), k
     return out
 
 
