@@ -1255,6 +1255,14 @@ BO_API int bo_render(const BoScene* sc, const BnRenderParams* p, float* film, ui
   return 0;
 }
 
+// CameraBase.GeneratePrimaryRay from explicit samples (tests/test_oracle_pssmlt_chain.py): u = uPixel.xy, uLens.xy.
+BO_API void bo_camera_ray(const BoScene* sc, int width, int height, int x, int y, const float* u, BnRay* out) {
+  const Ray r = primary_ray(sc->s.cam, width, height, x, y, V2{u[0], u[1]}, V2{u[2], u[3]});
+  out->origin[0] = r.o.x; out->origin[1] = r.o.y; out->origin[2] = r.o.z;
+  out->direction[0] = r.d.x; out->direction[1] = r.d.y; out->direction[2] = r.d.z;
+  out->tmax = INFINITY;
+}
+
 // MLTSampler driven by a script (tests/test_oracle_mlt_sampler.py): ops 0 = StartIteration, 1 = Next1D (its value is
 // appended to `out`), 2 = Accept, 3 = Reject.  Returns the number of values written.
 BO_API int bo_mlt_sampler_script(uint32_t seed_state, float large_step_prob, int strategy, float p0, float p1, const int32_t* script, int n,

@@ -53,6 +53,7 @@ def load() -> C.CDLL:
         lib.bo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.bo_set_portable_math.argtypes = [C.c_int]
         lib.bo_mlt_sampler_script.argtypes = [C.c_uint32, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.bo_camera_ray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.bo_light_eval_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.bo_light_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         lib.bo_material_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -96,6 +97,13 @@ class OracleScene:
         out = np.zeros(12, dtype=np.float32)
         hit = self._lib.bo_closest_geom(self._h, ray.ctypes.data, out.ctypes.data)
         return bool(hit), out.reshape(4, 3)
+
+    def camera_ray(self, width: int, height: int, x: int, y: int, u_pixel, u_lens) -> np.ndarray:
+        """CameraBase.GeneratePrimaryRay(resolution, (x, y), uPixel, uLens) as a one-element ray batch."""
+        u = np.array([u_pixel[0], u_pixel[1], u_lens[0], u_lens[1]], dtype=np.float32)
+        out = np.zeros(1, dtype=RAY_DTYPE)
+        self._lib.bo_camera_ray(self._h, width, height, x, y, u.ctypes.data, out.ctypes.data)
+        return out
 
     def light_eval_hit(self, ray: np.ndarray):
         """UniformLightSampler.Eval(ray.Origin, interaction) at the closest hit: (L xyz, pdf), or None if not an emitter."""
