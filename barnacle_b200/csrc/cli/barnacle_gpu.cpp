@@ -34,30 +34,44 @@ int main(int argc, char** argv) {
   std::printf("Loaded scene from %s\n", input.c_str());
   BnHostSceneInfo info{};
   bn_host_scene_info(host, &info);
-  // Loader.fs:185-188 order (normal, direct, path-tracing, pssmlt) -> BN_INTEGRATOR_*
-  int integrator;
-  if (info.integrator == 2) integrator = BN_INTEGRATOR_PATH_TRACING;
-  else if (info.integrator == 1) integrator = BN_INTEGRATOR_DIRECT;
-  else if (info.integrator == 0) integrator = BN_INTEGRATOR_NORMAL;
-  else {
-    std::fprintf(stderr, "integrator type %d (pssmlt) is outside the GPU hot path\n", info.integrator);
-    return 3;
-  }
   BnScene* scene = nullptr;
   if (bn_scene_create(bn_host_scene_desc(host), device, &scene) != BN_OK) return fail("bn_scene_create");
-  BnRenderParams p{};
-  p.width = info.width; p.height = info.height; p.spp = info.spp; p.max_depth = info.max_depth; p.rr_depth = info.rr_depth;
-  p.sample_begin = 0; p.sample_end = info.spp; p.x0 = 0; p.y0 = 0; p.x1 = info.width; p.y1 = info.height;
-  p.interleave_count = 1;
-  p.integrator = integrator;
-  std::vector<float> film((size_t)info.width * info.height * 3);
-  BnStats st{};
-  auto t0 = std::chrono::steady_clock::now();
-  if (bn_render(scene, &p, film.data(), &st) != BN_OK) return fail("bn_render");
-  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  std::printf("Render time: %f seconds\n", sec);
-  std::printf("paths %llu, rays %llu (%.1f Mrays/s on the device)\n", (unsigned long long)st.paths,
-              (unsigned long long)(st.extend_rays + st.shadow_rays), (st.extend_rays + st.shadow_rays) / (st.gpu_ms * 1e3));
+  std::vector<float> film((size_t)info.width * info.height * 3, 0.f);  // Film.Clear (Render.fs:11)
+  // Loader.fs:185-204 order: 0 normal, 1 direct, 2 path-tracing, 3 pssmlt
+  if (info.integrator == 3) {
+    BnMltParams p{};
+    p.width = info.width; p.height = info.height; p.mutations_per_pixel = info.spp; p.max_depth = info.max_depth; p.rr_depth = info.rr_depth;
+    p.n_bootstrap = info.n_bootstrap; p.n_chains = info.n_chains; p.strategy = info.mutation_strategy;
+    if (p.strategy == BN_MLT_KELEMEN) { p.p0 = 1.f / 1024.f; p.p1 = 1.f / 16.f; }  // MutationStrategy.Kelemen(1/1024, 1/16), Loader.fs:199
+    else { p.p0 = 1e-2f; }                                                          // MutationStrategy.Gaussian(1e-2), Loader.fs:195,198
+    p.large_step_prob = info.large_step_prob;
+    p.chain_begin = 0; p.chain_end = info.n_chains;
+    BnMltStats st{};
+    auto t0 = std::chrono::steady_clock::now();
+    if (bn_render_pssmlt(scene, &p, film.data(), &st) != BN_OK) return fail("bn_render_pssmlt");
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (st.b == 0.f) {
+      std::printf("Warning: all bootstrap samples are zero, exiting...\n");  // PSSMLT.fs:396-397
+    } else {  // PSSMLT.fs:412-414
+      std::printf("Accepted mutation count: %llu\n", (unsigned long long)st.accepted);
+      std::printf("Proposed mutation count: %llu\n", (unsigned long long)st.proposed);
+      std::printf("Acceptance rate: %f\n", (double)st.accepted / (double)(st.proposed ? st.proposed : 1));
+    }
+    std::printf("Render time: %f seconds\n", sec);
+  } else {
+    BnRenderParams p{};
+    p.width = info.width; p.height = info.height; p.spp = info.spp; p.max_depth = info.max_depth; p.rr_depth = info.rr_depth;
+    p.sample_begin = 0; p.sample_end = info.spp; p.x0 = 0; p.y0 = 0; p.x1 = info.width; p.y1 = info.height;
+    p.interleave_count = 1;
+    p.integrator = info.integrator == 2 ? BN_INTEGRATOR_PATH_TRACING : (info.integrator == 1 ? BN_INTEGRATOR_DIRECT : BN_INTEGRATOR_NORMAL);
+    BnStats st{};
+    auto t0 = std::chrono::steady_clock::now();
+    if (bn_render(scene, &p, film.data(), &st) != BN_OK) return fail("bn_render");
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("Render time: %f seconds\n", sec);
+    std::printf("paths %llu, rays %llu (%.1f Mrays/s on the device)\n", (unsigned long long)st.paths,
+                (unsigned long long)(st.extend_rays + st.shadow_rays), (st.extend_rays + st.shadow_rays) / (st.gpu_ms * 1e3));
+  }
   FILE* f = std::fopen(output.c_str(), "wb");
   if (!f) { std::fprintf(stderr, "cannot write %s\n", output.c_str()); return 4; }
   if (output.size() > 4 && output.substr(output.size() - 4) == ".pfm") {

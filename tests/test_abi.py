@@ -131,3 +131,20 @@ def test_fsharp_binding_imports_only_declared_symbols(root):
     imported = set(re.findall(r"extern \w+ (bn_\w+)\(", text))
     assert imported and imported <= set(_ffi.SYMBOLS)
     assert {"bn_scene_create", "bn_scene_destroy", "bn_render", "bn_render_pssmlt", "bn_last_error"} <= imported
+
+
+# ---- the C++ caller that mirrors Program.fs (barnacle_b200/csrc/cli/barnacle_gpu.cpp) -----------------------------
+def test_cli_mirrors_program_fs_argument_and_error_behaviour(lib, root, tmp_path):
+    import subprocess
+    exe = os.path.join(root, "barnacle_b200", "lib", "barnacle_gpu")
+    assert os.path.exists(exe), "the build step links the CLI next to the library"
+    run = lambda *a: subprocess.run([exe, *a], cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    r = run("-o", "x.ppm")                                            # Program.fs:24: failwith "Invalid arguments."
+    assert r.returncode != 0 and "Invalid arguments." in r.stderr
+    r = run("-i", "scenes/does_not_exist.json", "-o", str(tmp_path / "x.ppm"))
+    assert r.returncode != 0 and "cannot open" in r.stderr
+    if lib.bn_device_count() == 0:                                    # no CPU fallback: loud failure after a successful load
+        for scene in ("scenes/cbox_pt.json", "scenes/cbox_mlt.json"):
+            r = run("-i", scene, "-o", str(tmp_path / "x.ppm"), "--base-dir", root)
+            assert r.returncode != 0 and "Loaded scene from" in r.stdout and "no CUDA device" in r.stderr
+            assert not (tmp_path / "x.ppm").exists()
