@@ -390,7 +390,14 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
           const Slab sr = slab<true>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
           const bool pl = slab_pass<true>(sl, t), pr = slab_pass<true>(sr, t);
           const uint32_t level = cur & kTlasBit;
+#ifdef BN_EXP_ANY_UNORDERED
+          // experiment queued for the next GPU session (default off): an any-hit query returns the same boolean whatever
+          // the visiting order (every box that passes is visited unless a hit ends the walk first), so shadow rays could
+          // skip the front-to-back bookkeeping: unoccluded rays save instructions, occluded ones may walk further
+          const bool lf = ANY ? true : ((signs >> fbits(n3.z)) & 1u) != 0u;
+#else
           const bool lf = ((signs >> fbits(n3.z)) & 1u) != 0u;  // left first iff dir[splitAxis] > 0 (BVH.fs:51-56 / Mesh.fs:235-240)
+#endif
           const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
           if (!pl) {  // branches on the two predicates as they are (no pl | pr to materialise)
             if (pr) cur = right;
