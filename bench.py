@@ -99,7 +99,7 @@ class ClockSampler:
                 "samples": len(rows), "reasons": reasons}
 
 
-def oracle_sample(scene, w, h, spp_sample, counters: bool, libm: bool = True):
+def oracle_sample(scene, w, h, spp_sample, counters: bool, libm: bool = True, keep_film: bool = False):
     """The CPU restatement on a bounded sample of the workload (all host threads)."""
     from barnacle_b200.scene import make_params
     from oracle.oracle_ffi import OracleScene, num_threads, set_portable_math
@@ -107,11 +107,24 @@ def oracle_sample(scene, w, h, spp_sample, counters: bool, libm: bool = True):
     try:
         o = OracleScene(scene.desc)
         p = make_params(w, h, spp_sample, MAX_DEPTH, RR_DEPTH)
-        _, st = o.render(p, counters=counters)
+        film, st = o.render(p, counters=counters)
     finally:
         set_portable_math(True)
     st["threads"] = num_threads()
+    if keep_film:
+        st["film"] = film
     return st
+
+
+def rel_mse(image, reference, eps=1e-2):
+    """mean over pixels and channels of (I - R)^2 / (R^2 + eps); pixels that are not finite in either image are left out
+    and counted (PSSMLT-style NaN pixels do not occur in path tracing, but a metric must say so rather than hide it)."""
+    import numpy as np
+    a, b = np.asarray(image, dtype=np.float64).reshape(-1, 3), np.asarray(reference, dtype=np.float64).reshape(-1, 3)
+    ok = np.isfinite(a).all(axis=1) & np.isfinite(b).all(axis=1)
+    if not ok.any():
+        return None, int((~ok).sum())
+    return float((((a[ok] - b[ok]) ** 2) / (b[ok] ** 2 + eps)).mean()), int((~ok).sum())
 
 
 def run_reference(args, scene_file, W, H, SPP, label):
@@ -424,15 +437,25 @@ def main():
         if _ffi.load().bn_measure_l2_read_gbs(local, 32 << 20, 20, ctypes.byref(l2)) == 0 and l2.value > 0 and achieved:
             roofline["l2"] = {"peak": l2.value, "unit": "GB/s", "frac": achieved / l2.value,
                               "peak_source": "bn_measure_l2_read_gbs: 20 sweeps of a 32 MiB L2-resident buffer, ld.global.cg.v4, CUDA events, this run"}
-        cpu = None
+        cpu = relmse = None
         if not args.no_cpu_baseline and world == 1:
             # ~10-30 s of CPU work on all host threads: about 30 M paths of the workload's film (libm math, as the reference)
             cpu_spp = max(1, min(SPP, -(-30_000_000 // (W * H))))
-            cs = oracle_sample(scene, W, H, cpu_spp, False)
+            cs = oracle_sample(scene, W, H, cpu_spp, False, keep_film=True)
             cpu = {"value": (cs["extend_rays"] + cs["shadow_rays"]) / cs["seconds"] / 1e6, "unit": "Mrays/s", "cores": cs["threads"], "kind": "port",
                    "samples_per_s": cs["paths"] / cs["seconds"],
                    "sample": f"{W}x{H} at {cpu_spp} of {SPP} spp ({cs['seconds']:.1f} s); rays = extend + shadow rays the reference traces",
                    "note": "C++ restatement of Barnacle's CPU path (the .NET binary is not runnable in this image)"}
+            # BASELINE's second metric, relMSE of the linear film against the CPU path under identical seeds: the same
+            # sample of the workload rendered here on the GPU (outside every timed region) against the film just made
+            try:
+                gfilm, _ = gpu.render(make_params(W, H, cpu_spp, MAX_DEPTH, RR_DEPTH))
+                v, skipped = rel_mse(gfilm, cs["film"])
+                relmse = {"value": v, "eps": 1e-2, "non_finite_pixels_skipped": skipped,
+                          "vs": f"CPU restatement (libm transcendentals, as the reference) on the same seeds, {W}x{H} at {cpu_spp} spp; "
+                                "against the restatement with this library's fixed fp32 transcendentals the film is bit-identical (tests/)"}
+            except Exception as e:  # a metric must never take the bench line down with it
+                relmse = {"value": None, "error": f"{type(e).__name__}: {e}"}
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -444,7 +467,7 @@ def main():
             "gpu_launches": launches_total,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
                     "rank0_step_ms": [round(x, 2) for x in e2e_step_ms]},
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "relmse": relmse,
         }
         print(json.dumps(out))
     if world > 1:
