@@ -15,14 +15,17 @@
 // its box; `tmin <= Min(t, thi)` == `(tmin <= t) && (tmin <= thi)`.
 //
 // Execution model: a persistent, warp-synchronous loop.  Every lane owns one ray
-// and is in one of three states; each iteration the warp votes and runs the ONE
+// and is in one of four states; each iteration the warp votes and runs the ONE
 // phase most lanes are ready for, so that lanes doing the same kind of work do it
 // together (SIMT efficiency is what bounds this kernel, not DRAM):
 //   N  one node step (64-B GNode, two slab tests)
 //   E  enter instance: ray -> object space, BLAS root / sphere test
 //   T  the next triangle of the held BLAS leaf
-// Lanes whose ray is finished are refilled from the global queue (one
-// warp-aggregated atomic) as soon as enough of them are idle.
+//   S  small TLAS only: the next candidate of the octant-ordered instance list
+// Phases N and T, once chosen, repeat on a single ballot while enough lanes still
+// have that kind of work (kStayMin / kStayT).  Lanes whose ray is finished are
+// refilled from the global queue (one warp-aggregated atomic) as soon as enough of
+// them are idle (kRefillMin / kRefillMinAny).
 //
 // The phases run the FAST slab form (vecmath.cuh), which is bit-identical to the
 // reference's for every ray whose 1/d has only finite non-zero components.  A ray
