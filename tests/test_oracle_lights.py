@@ -148,3 +148,64 @@ def test_two_lights_alias_quirk_and_transformed_sphere(lib):
     assert all(l == (f > 0) for l, f in zip(lit, facing) if abs(f) > 1e-3) and any(lit) and not all(lit)
     inside = oracle.light_sample(np.array([5.0, 1.0, -2.0], dtype=np.float32), (1 - quad_slot + 0.5) / 2, [0.2, 0.7])
     assert not inside[3:6].any()                                          # from its centre every point faces away
+
+
+def ref_light_eval(desc, inst, origin, p, n, t, b):
+    """UniformLightSampler.Eval (Uniform.fs:40-49) with MeshInstance.EvalPDF (Mesh.fs:300-304; the tag is always 0 after
+    LocalGeometry.Transform) and SphereInstance.EvalPDF (Sphere.fs:115-126), float64."""
+    n_lights = desc.light_instance_count
+    if inst.prim_kind == 0:
+        m = desc.meshes[inst.prim_id]
+        o2w = _mat(inst, "object_to_world")
+
+        def vertex(k):
+            v = 3 * (m.vertex_offset + desc.triangles[3 * m.tri_offset + k])
+            return np.array([desc.vertices[v], desc.vertices[v + 1], desc.vertices[v + 2]], dtype=np.float64) @ o2w[:3, :3] + o2w[3, :3]
+        p0, p1, p2 = vertex(0), vertex(1), vertex(2)
+        pdf_surface = desc.alias[m.alias_offset].pdf / (0.5 * np.linalg.norm(np.cross(p1 - p0, p2 - p0)))
+    else:
+        w2o = _mat(inst, "world_to_object")
+        radius = float(desc.sphere_radii[inst.prim_id])
+        pdf_surface = np.linalg.norm(np.cross(t @ w2o[:3, :3], b @ w2o[:3, :3])) / (4 * math.pi * radius * radius)
+    wo = (origin - p) / np.linalg.norm(origin - p)
+    cos_wo = float(n @ wo)
+    return _diffuse_light_eval(desc.lights[inst.light_id], cos_wo), float((origin - p) @ (origin - p)) * pdf_surface / (max(abs(cos_wo), 1e-6) * n_lights), cos_wo
+
+
+def test_light_eval_at_emitter_hits_matches_restatement(lib):
+    """The MIS side: a BSDF-sampled ray that lands on an emitter is weighted with UniformLightSampler.Eval's pdf."""
+    from barnacle_b200.scene import RAY_DTYPE
+    tr = [{"keyframes": [{"scale": [1.0, 2.0, 0.5], "rotation": [0.4, 0.0, -0.3], "translation": [5.0, 1.0, -2.0]}]},
+          {"keyframes": [{"scale": [3.0, 1.0, 2.0], "translation": [-4.0, 6.0, 0.0]}]}]
+    text = _scene([{"type": "quad"}, {"type": "sphere", "radius": 1.5}],
+                  [{"primitive": 0, "light": 0}, {"primitive": 1, "light": 1}],
+                  [{"children": [1, 2, 3]}, {"instances": [0], "transform": 1}, {"instances": [1], "transform": 0}, {"has-camera": True}],
+                  tr, [{"type": "diffuse", "emission": [3.0, 2.0, 1.0]}, {"type": "diffuse", "emission": [1.0, 4.0, 9.0], "two-sided": False}])
+    scene = Scene.LoadString(text)
+    desc = scene.desc.contents
+    oracle = OracleScene(scene.desc)
+    rng = np.random.default_rng(21)
+    checked = {0: 0, 1: 0}
+    for _ in range(600):
+        k = int(rng.integers(0, 2))
+        inst = desc.instances[k]
+        lo, hi = np.array(inst.bounds_min[:]), np.array(inst.bounds_max[:])
+        origin = rng.uniform(-10, 10, size=3)
+        target = lo + (hi - lo) * rng.random(3)
+        d = (target - origin) / np.linalg.norm(target - origin)
+        ray = np.zeros(1, dtype=RAY_DTYPE)
+        ray[0] = (origin.astype(np.float32), d.astype(np.float32), np.inf)
+        got = oracle.light_eval_hit(ray)
+        if got is None:
+            continue
+        hit = oracle.trace(ray)[0]
+        _, g = oracle.closest_geom(ray)
+        p, n, t, b = (g[j].astype(np.float64) for j in range(4))
+        hit_inst = desc.instances[int(hit["instance"])]
+        L, pdf, cos_wo = ref_light_eval(desc, hit_inst, ray["origin"][0].astype(np.float64), p, n, t, b)
+        if abs(cos_wo) < 1e-3:
+            continue
+        np.testing.assert_allclose(got[:3], L, rtol=1e-6)
+        assert got[3] == pytest.approx(pdf, rel=5e-4)
+        checked[hit_inst.prim_kind] += 1
+    assert checked[0] > 50 and checked[1] > 50, checked
