@@ -178,3 +178,21 @@ def test_direct_and_normal_integrators_match_restatement(scene_loader, oracle_li
                 exact += np.array_equal(got.view(np.uint32), ref.view(np.uint32))
                 lit += bool(np.nan_to_num(ref).any())
     assert lit > 0.5 * n and exact >= 0.98 * n, (lit, exact, n)
+
+
+def test_film_is_the_fma_chain_of_the_per_sample_radiance(scene_loader, oracle_lib):
+    """ProgressiveIntegrator.RenderTile (Integrator.fs:29-44) + Film.SetPixel (Film.fs:41-46): per pixel,
+    accum = fma(1/spp, Li * 1/pdf, accum) over sampleId ascending, stored at the Y-flipped index."""
+    oracle_ffi.set_portable_math(False)
+    scene = scene_loader("cbox_pt")
+    oracle = OracleScene(scene.desc)
+    w, h, spp = 24, 18, 5
+    p = make_params(w, h, spp)
+    film, _ = oracle.render(p, threads=1)
+    rad = oracle.render_radiance(p, threads=1)                           # [spp, h, w, 3], row y = image row y
+    inv = F(F(1) / F(spp))
+    acc = np.zeros((h, w, 3), F)
+    for s in range(spp):
+        acc = (np.float64(inv) * rad[s].astype(np.float64) + acc.astype(np.float64)).astype(F)
+    want = acc[::-1].reshape(h * w, 3)                                   # index (H - y - 1) * W + x
+    np.testing.assert_array_equal(film.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
