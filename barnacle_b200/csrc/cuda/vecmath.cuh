@@ -7,6 +7,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#ifdef BN_EXP_SHARED_RCP
+#include "../../../include/bn_portable_math.h"
+#endif
 
 #ifndef BN_NET9_FMA
 #define BN_NET9_FMA 1
@@ -38,7 +41,19 @@ BN_DEV float div_ieee(float a, float s) {
   const float q = (zero_num ? 1.f : a) / s;
   return zero_num ? __uint_as_float((__float_as_uint(a) ^ __float_as_uint(s)) & 0x80000000u) : q;
 }
+#ifdef BN_EXP_SHARED_RCP
+// experiment queued for the next GPU session (default off): the three divisions of a normalize() share one correctly
+// rounded reciprocal (include/bn_portable_math.h: bn_div_by_rcp — same bits as the IEEE division on the guarded domain)
+static __device__ __noinline__ float3 div3_ieee(float3 a, float s) { return f3(div_ieee(a.x, s), div_ieee(a.y, s), div_ieee(a.z, s)); }  // one cold copy
+BN_DEV float3 operator/(float3 a, float s) {
+  const bool ok = bn_div_rcp_ok(s) && (a.x == 0.f || bn_div_rcp_ok(a.x)) && (a.y == 0.f || bn_div_rcp_ok(a.y)) && (a.z == 0.f || bn_div_rcp_ok(a.z));
+  if (!ok) return div3_ieee(a, s);
+  const float r = __frcp_rn(s);
+  return f3(bn_div_by_rcp(a.x, s, r), bn_div_by_rcp(a.y, s, r), bn_div_by_rcp(a.z, s, r));
+}
+#else
 BN_DEV float3 operator/(float3 a, float s) { return f3(div_ieee(a.x, s), div_ieee(a.y, s), div_ieee(a.z, s)); }
+#endif
 // Vector3.FusedMultiplyAdd
 BN_DEV float3 vfma(float3 a, float3 b, float3 c) { return f3(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y), __fmaf_rn(a.z, b.z, c.z)); }
 // Vector3.Dot: ((x*x' + y*y') + z*z')

@@ -115,4 +115,23 @@ BN_HD float bn_expf(float x) {
   return r * bn_uint_as_float((unsigned int)(n + 127) << 23);   /* ldexp(r, n), -126 <= n <= 127 */
 }
 
+/* ---- a / s for several numerators sharing ONE correctly rounded reciprocal ---------------------------------
+ * (experiment for the shade kernel's normalize(), default off: -DBN_EXP_SHARED_RCP in vecmath.cuh)
+ * With r = RN(1 / s):  q0 = RN(a r),  rem = fma(-s, q0, a) (exact),  q = fma(rem, r, q0)  is the correctly rounded
+ * quotient RN(a / s) — Markstein's theorem — as long as nothing under- or overflows on the way, so the result has
+ * the SAME BITS as the IEEE division the reference performs.  bn_div_rcp_ok() states the domain this is used on
+ * (|x| in [2^-60, 2^60], or a zero numerator, whose sign the quotient keeps); tests/test_shared_rcp.py checks the
+ * identity there on 4 x 10^7 operand pairs incl. all-ones and near-power-of-two mantissas, and shows it FAILS
+ * outside (numerators near the smallest normal), which is why the caller falls back to plain division there. */
+BN_HD int bn_div_rcp_ok(float x) {
+  float m = fabsf(x);
+  return (m >= 8.67361737988403547e-19f && m <= 1.15292150460684698e18f) ? 1 : 0;   /* 2^-60 .. 2^60 */
+}
+BN_HD float bn_div_by_rcp(float a, float s, float r) {
+  float q0 = a * r;
+  float rem = fmaf(-s, q0, a);
+  float q = fmaf(rem, r, q0);
+  return q0 == 0.0f ? q0 : q;   /* a == +-0: keep the zero with its sign (fma(+0, r, -0) would lose it) */
+}
+
 #endif /* BN_PORTABLE_MATH_H */
