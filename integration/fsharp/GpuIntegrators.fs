@@ -184,6 +184,10 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int bn_render_pssmlt(nativeint scene, BnMltParams& p, nativeint filmRgb, BnMltStats& stats)
 
+    /// BVHNode.Build on the device (optional, "next" row N2): same nodes and permutation as Util/BVH.fs:239-247, byte for byte.
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int bn_bvh_build(int device, nativeint boxes, uint32 n, nativeint nodes, uint32 maxNodes, nativeint perm, nativeint ms)
+
     /// The reference's error convention is `failwith` (Base/LightSampler.fs:8-9, Loader.fs:204 ...).
     let check (rc: int) =
         if rc <> 0 then
@@ -195,6 +199,34 @@ type IGpuIntegrator =
     /// Scene.Traverse(t)'s result in its ORIGINAL order (a copy taken before BVHAggregate permutes the
     /// array in place, Extensions/Aggregate/BVH.fs:9 + Util/BVH.fs:244-246).
     abstract member Instances: PrimitiveInstance array with get, set
+
+/// Drop-in for BVHNode.Build (Util/BVH.fs:239-247) that runs the binned-SAH build on the GPU: permutes `xs` in place,
+/// returns the preorder node array.  Boxes must be finite (anything else fails loudly; keep the host builder for those).
+module GpuBvh =
+    let build (device: int) (xs: 'a Span) (f: 'a -> AxisAlignedBoundingBox) : BVHNode array =
+        let xs' = xs.ToArray()
+        let boxes = Array.zeroCreate<float32> (6 * xs'.Length)
+        for i = 0 to xs'.Length - 1 do
+            let b = f xs'[i]
+            boxes[6 * i] <- b.pMin.X
+            boxes[6 * i + 1] <- b.pMin.Y
+            boxes[6 * i + 2] <- b.pMin.Z
+            boxes[6 * i + 3] <- b.pMax.X
+            boxes[6 * i + 4] <- b.pMax.Y
+            boxes[6 * i + 5] <- b.pMax.Z
+        let nodes = Array.zeroCreate<BVHNode> (max 1 (2 * xs'.Length))
+        let perm = Array.zeroCreate<uint32> xs'.Length
+        use pBoxes = fixed boxes
+        use pNodes = fixed nodes // pinned, not marshalled: BVHNode holds a bool, which the marshaller would widen
+        use pPerm = fixed perm
+        let count =
+            Native.bn_bvh_build (device, NativePtr.toNativeInt pBoxes, uint32 xs'.Length, NativePtr.toNativeInt pNodes,
+                                 uint32 nodes.Length, NativePtr.toNativeInt pPerm, 0n)
+        if count < 0 then
+            failwith (Marshal.PtrToStringUTF8(Native.bn_last_error ()))
+        for i = 0 to xs'.Length - 1 do
+            xs[i] <- xs'[int perm[i]] // Util/BVH.fs:244-246
+        Array.sub nodes 0 count
 
 /// Flattens the managed object graph into the POD arrays of BnSceneDesc and keeps them pinned for the
 /// duration of `body`.  Reads public members only.
