@@ -202,31 +202,33 @@ type IGpuIntegrator =
 
 /// Drop-in for BVHNode.Build (Util/BVH.fs:239-247) that runs the binned-SAH build on the GPU: permutes `xs` in place,
 /// returns the preorder node array.  Boxes must be finite (anything else fails loudly; keep the host builder for those).
-module GpuBvh =
-    let build (device: int) (xs: 'a Span) (f: 'a -> AxisAlignedBoundingBox) : BVHNode array =
-        let xs' = xs.ToArray()
-        let boxes = Array.zeroCreate<float32> (6 * xs'.Length)
-        for i = 0 to xs'.Length - 1 do
-            let b = f xs'[i]
-            boxes[6 * i] <- b.pMin.X
-            boxes[6 * i + 1] <- b.pMin.Y
-            boxes[6 * i + 2] <- b.pMin.Z
-            boxes[6 * i + 3] <- b.pMax.X
-            boxes[6 * i + 4] <- b.pMax.Y
-            boxes[6 * i + 5] <- b.pMax.Z
-        let nodes = Array.zeroCreate<BVHNode> (max 1 (2 * xs'.Length))
-        let perm = Array.zeroCreate<uint32> xs'.Length
-        use pBoxes = fixed boxes
-        use pNodes = fixed nodes // pinned, not marshalled: BVHNode holds a bool, which the marshaller would widen
-        use pPerm = fixed perm
-        let count =
-            Native.bn_bvh_build (device, NativePtr.toNativeInt pBoxes, uint32 xs'.Length, NativePtr.toNativeInt pNodes,
-                                 uint32 nodes.Length, NativePtr.toNativeInt pPerm, 0n)
-        if count < 0 then
-            failwith (Marshal.PtrToStringUTF8(Native.bn_last_error ()))
-        for i = 0 to xs'.Length - 1 do
-            xs[i] <- xs'[int perm[i]] // Util/BVH.fs:244-246
-        Array.sub nodes 0 count
+[<AbstractClass; Sealed>]
+type GpuBvh =
+    /// A tupled static member like BVHNode.Build itself: Span is byref-like and cannot be a curried argument.
+    static member Build(device: int, xs: 'a Span, f: 'a -> AxisAlignedBoundingBox) : BVHNode array =
+            let xs' = xs.ToArray()
+            let boxes = Array.zeroCreate<float32> (6 * xs'.Length)
+            for i = 0 to xs'.Length - 1 do
+                let b = f xs'[i]
+                boxes[6 * i] <- b.pMin.X
+                boxes[6 * i + 1] <- b.pMin.Y
+                boxes[6 * i + 2] <- b.pMin.Z
+                boxes[6 * i + 3] <- b.pMax.X
+                boxes[6 * i + 4] <- b.pMax.Y
+                boxes[6 * i + 5] <- b.pMax.Z
+            let nodes = Array.zeroCreate<BVHNode> (max 1 (2 * xs'.Length))
+            let perm = Array.zeroCreate<uint32> xs'.Length
+            use pBoxes = fixed boxes
+            use pNodes = fixed nodes // pinned, not marshalled: BVHNode holds a bool, which the marshaller would widen
+            use pPerm = fixed perm
+            let count =
+                Native.bn_bvh_build (device, NativePtr.toNativeInt pBoxes, uint32 xs'.Length, NativePtr.toNativeInt pNodes,
+                                     uint32 nodes.Length, NativePtr.toNativeInt pPerm, 0n)
+            if count < 0 then
+                failwith (Marshal.PtrToStringUTF8(Native.bn_last_error ()))
+            for i = 0 to xs'.Length - 1 do
+                xs[i] <- xs'[int perm[i]] // Util/BVH.fs:244-246
+            Array.sub nodes 0 count
 
 /// Flattens the managed object graph into the POD arrays of BnSceneDesc and keeps them pinned for the
 /// duration of `body`.  Reads public members only.
