@@ -427,6 +427,8 @@ type GpuProgressiveIntegrator(spp: int, maxDepth: int, rrDepth: int, kind: int) 
             and set v = instances <- v
 
     override this.Render(camera, film, _aggregate, lightSampler) =
+        use pixels = fixed film.Pixels // Vector3[W*H] == float[3*W*H], already Y-flipped (Film.fs:41-46); pinned for the whole call
+        let filmRgb = NativePtr.toNativeInt pixels
         GpuScene.withDeviceScene camera lightSampler instances this.Device (fun scene ->
             let mutable p = Native.BnRenderParams()
             p.width <- film.ImageWidth
@@ -446,8 +448,7 @@ type GpuProgressiveIntegrator(spp: int, maxDepth: int, rrDepth: int, kind: int) 
             p.interleaveIndex <- 0
             p.integrator <- kind
             let mutable stats = Native.BnStats()
-            use pixels = fixed film.Pixels // Vector3[W*H] == float[3*W*H], already Y-flipped (Film.fs:41-46)
-            Native.check (Native.bn_render (scene, &p, NativePtr.toNativeInt pixels, &stats))
+            Native.check (Native.bn_render (scene, &p, filmRgb, &stats))
             this.LastStats <- stats)
         this.FrameId <- this.FrameId + 1 // Integrator.fs:55
 
@@ -468,6 +469,8 @@ type GpuPSSMLTIntegrator
             and set v = instances <- v
 
     override this.Render(camera, film, _aggregate, lightSampler) = // FrameId is not advanced (PSSMLT.fs:379-414 never does)
+        use pixels = fixed film.Pixels // accumulated INTO, like Film.Accumulate; Scene.Render cleared it
+        let filmRgb = NativePtr.toNativeInt pixels
         GpuScene.withDeviceScene camera lightSampler instances this.Device (fun scene ->
             let mutable p = Native.BnMltParams()
             p.width <- film.ImageWidth
@@ -490,8 +493,7 @@ type GpuPSSMLTIntegrator
             p.chainBegin <- 0
             p.chainEnd <- nChains
             let mutable stats = Native.BnMltStats()
-            use pixels = fixed film.Pixels // accumulated INTO, like Film.Accumulate; Scene.Render cleared it
-            Native.check (Native.bn_render_pssmlt (scene, &p, NativePtr.toNativeInt pixels, &stats))
+            Native.check (Native.bn_render_pssmlt (scene, &p, filmRgb, &stats))
             this.B <- stats.b
             this.AcceptedMutationCount <- int64 stats.accepted
             this.ProposedMutationCount <- int64 stats.proposed
