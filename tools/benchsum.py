@@ -1,3 +1,4 @@
+"""One-line summary of a bench.py JSON line on stdin (value, ms per step, per-class ms, extend / shadow rays per second, e2e)."""
 import sys,json
 for l in sys.stdin:
     if l.startswith("{"):
