@@ -75,6 +75,20 @@ BN_DEV float3 min_native(float3 a, float3 b) { return f3(min_native(a.x, b.x), m
 BN_DEV float3 max_native(float3 a, float3 b) { return f3(max_native(a.x, b.x), max_native(a.y, b.y), max_native(a.z, b.z)); }
 // Math.Max / Math.Min / MathF.Max / MathF.Min: IEEE 754-2019 maximum/minimum
 // (NaN-propagating, +0 > -0) — one instruction on sm_100.
+#ifdef BN_HOSTSIM
+// host build of these device functions for tests/hostsim (never part of the product): the same IEEE 754-2019
+// maximum / minimum spelled out
+BN_DEV float net_max(float a, float b) {
+  if (a != a || b != b) return __uint_as_float(0x7fffffffu);  // max.NaN.f32 returns the canonical NaN
+  if (a == b) return (__float_as_uint(a) & 0x80000000u) ? b : a;  // +0 > -0
+  return a > b ? a : b;
+}
+BN_DEV float net_min(float a, float b) {
+  if (a != a || b != b) return __uint_as_float(0x7fffffffu);
+  if (a == b) return (__float_as_uint(a) & 0x80000000u) ? a : b;
+  return a < b ? a : b;
+}
+#else
 BN_DEV float net_max(float a, float b) {
   float r;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -85,6 +99,7 @@ BN_DEV float net_min(float a, float b) {
   asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
+#endif
 
 // 4x3 slice of a row-major Matrix4x4 (rows M1x..M4x, columns 1..3): all that
 // Vector3.Transform reads.

@@ -1,0 +1,192 @@
+"""The GPU path's own device functions, compiled for the HOST (tests/hostsim/), against the oracle — bit for bit.
+
+traverse.cuh's per-lane walk in its fast and exact slab forms over the converted device layout (64-B two-box nodes,
+pre-gathered triangles, pseudo nodes for multi-instance TLAS leaves), and shade.cuh's camera, material and light-sampler
+functions, are plain C++ once the CUDA intrinsics are spelled as the IEEE operations they are (device_shim.h).  This
+gives a CPU-side regression net for the arithmetic and the data layout of the CUDA path: an edit that breaks parity
+shows up here, before any GPU time is spent.  It does NOT replace the -m gpu tests (nvcc's code generation, the
+warp-synchronous phase loop and the wavefront are only exercised on the B200), and it is not a fallback: nothing in
+barnacle_b200/ can reach this code."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from barnacle_b200 import _ffi
+from barnacle_b200.scene import RAY_DTYPE, Scene, make_params
+from conftest import random_rays
+from oracle import oracle_ffi
+from oracle.oracle_ffi import HIT_DTYPE, OracleScene
+from test_oracle_bruteforce import _random_scene_json
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hs(root):
+    src = os.path.join(HERE, "hostsim")
+    out_dir = os.path.join(src, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    lib_path = os.path.join(out_dir, "libhostsim.so")
+    csrc = os.path.join(root, "barnacle_b200", "csrc", "cuda")
+    deps = [os.path.join(src, f) for f in ("hostsim.cpp", "device_shim.h")] + \
+           [os.path.join(csrc, f) for f in ("traverse.cuh", "shade.cuh", "vecmath.cuh", "device_scene.h", "scene_convert.cpp", "scene_convert.h", "traverse_limits.h")] + \
+           [os.path.join(root, "include", "bn_portable_math.h")]
+    if not os.path.exists(lib_path) or any(os.path.getmtime(d) > os.path.getmtime(lib_path) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+                        os.path.join(src, "hostsim.cpp"), os.path.join(csrc, "scene_convert.cpp"), "-o", lib_path], check=True)
+    lib = C.CDLL(lib_path)
+    lib.hs_scene_create.restype = C.c_void_p
+    lib.hs_scene_create.argtypes = [C.c_void_p]
+    lib.hs_scene_destroy.argtypes = [C.c_void_p]
+    lib.hs_last_error.restype = C.c_char_p
+    lib.hs_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.hs_camera_ray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.hs_material_eval.argtypes = [C.c_void_p] * 4
+    lib.hs_material_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    lib.hs_light_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    lib.hs_xxhash32_three.restype = C.c_uint32
+    lib.hs_xxhash32_three.argtypes = [C.c_uint32] * 3
+    lib.hs_lcg.restype = C.c_float
+    lib.hs_lcg.argtypes = [C.POINTER(C.c_uint32)]
+    return lib
+
+
+class HostScene:
+    def __init__(self, hs, scene):
+        self.hs = hs
+        self.h = hs.hs_scene_create(C.cast(scene.desc, C.c_void_p))
+        assert self.h, hs.hs_last_error()
+
+    def trace(self, rays, any_hit=False, mode=1):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        fast = C.c_uint64(0)
+        assert self.hs.hs_trace(self.h, rays.ctypes.data, len(rays), 1 if any_hit else 0, mode, hits.ctypes.data, C.byref(fast)) == 0
+        return hits, fast.value
+
+    def __del__(self):
+        self.hs.hs_scene_destroy(self.h)
+
+
+def _same_hits(desc, a, b):
+    assert np.array_equal(a["instance"], b["instance"])
+    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    hit = a["instance"] >= 0
+    mesh = np.zeros(len(a), dtype=bool)
+    mesh[hit] = [desc.instances[int(i)].prim_kind == 0 for i in a["instance"][hit]]
+    assert np.array_equal(a["primitive"][mesh], b["primitive"][mesh])
+    assert np.array_equal(a["u"][mesh].view(np.uint32), b["u"][mesh].view(np.uint32))
+    assert np.array_equal(a["v"][mesh].view(np.uint32), b["v"][mesh].view(np.uint32))
+
+
+def _adversarial(scene, n, seed):
+    """Axis-parallel directions (exact and signed zeros), origins on box faces: the NaN lanes of the slab test."""
+    rng = np.random.default_rng(seed)
+    rays = random_rays(scene, n, seed=seed)
+    d = rays["direction"].copy()
+    zero = rng.random((n, 3)) < 0.4
+    d[zero] = 0.0
+    d[zero & (rng.random((n, 3)) < 0.5)] = -0.0
+    d[np.all(d == 0, axis=1)] = [0.0, 0.0, 1.0]
+    rays["direction"] = d
+    desc = scene.desc.contents
+    pick = rng.integers(0, desc.instance_count, size=n)
+    face = rng.random(n) < 0.5
+    for k in np.flatnonzero(face):                                        # origin coordinate exactly on an instance box plane
+        inst = desc.instances[int(pick[k])]
+        ax = int(rng.integers(0, 3))
+        rays["origin"][k, ax] = inst.bounds_min[ax] if rng.random() < 0.5 else inst.bounds_max[ax]
+    return rays
+
+
+@pytest.mark.parametrize("name", ["cbox_pt", "cbox_bunny", "material_sweep", "bunny_instanced_small"])
+def test_device_traversal_on_the_host_equals_the_oracle(hs, scene_loader, name):
+    scene = scene_loader(name)
+    desc = scene.desc.contents
+    oracle, host = OracleScene(scene.desc), HostScene(hs, scene)
+    batches = {"primary": oracle.primary_rays(make_params(48, 48, 1)), "random": random_rays(scene, 6000, seed=3),
+               "adversarial": _adversarial(scene, 4000, seed=4)}
+    for label, rays in batches.items():
+        want = oracle.trace(rays)
+        for mode in (0, 1):
+            got, fast = host.trace(rays, mode=mode)
+            _same_hits(desc, got, want)
+            if mode == 1 and label != "adversarial":
+                assert fast > 0.99 * len(rays)                            # the fast slab form carries almost every ray
+        if label == "adversarial":
+            _, fast = host.trace(rays, mode=1)
+            assert fast < 0.9 * len(rays)                                 # ... and these really take the exact form
+        tm = rays.copy()
+        tm["tmax"] = np.where(want["instance"] >= 0, want["t"] * np.float32(1.5), np.float32(50.0))
+        tm["tmax"][::2] = np.where(want["instance"][::2] >= 0, want["t"][::2] * np.float32(0.5), np.float32(5.0))
+        want_any = oracle.trace(tm, any_hit=True)["instance"]
+        for mode in (0, 1):
+            assert np.array_equal(host.trace(tm, any_hit=True, mode=mode)[0]["instance"], want_any)
+
+
+@pytest.mark.parametrize("seed,n_instances", [(31, 2), (32, 14), (33, 60), (34, 250)])
+def test_device_traversal_on_randomised_scenes(hs, lib, seed, n_instances):
+    rng = np.random.default_rng(seed)
+    scene = Scene.LoadString(_random_scene_json(rng, n_instances))
+    desc = scene.desc.contents
+    oracle, host = OracleScene(scene.desc), HostScene(hs, scene)
+    rays = random_rays(scene, 3000, seed=seed)
+    pick = rng.integers(0, desc.instance_count, size=len(rays))
+    lo = np.array([desc.instances[int(k)].bounds_min[:] for k in pick], dtype=np.float64)
+    hi = np.array([desc.instances[int(k)].bounds_max[:] for k in pick], dtype=np.float64)
+    d = lo + (hi - lo) * rng.random((len(rays), 3)) - rays["origin"]
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    want = oracle.trace(rays)
+    assert (want["instance"] >= 0).mean() > 0.2
+    for mode in (0, 1):
+        _same_hits(desc, host.trace(rays, mode=mode)[0], want)
+    adv = _adversarial(scene, 2000, seed=seed + 100)
+    want = oracle.trace(adv)
+    for mode in (0, 1):
+        _same_hits(desc, host.trace(adv, mode=mode)[0], want)
+
+
+def test_device_shading_functions_on_the_host_equal_the_oracle(hs, scene_loader, oracle_lib):
+    oracle_ffi.set_portable_math(True)                                    # the fixed fp32 transcendentals the kernels evaluate
+    rng = np.random.default_rng(9)
+    # hash + LCG
+    for _ in range(200):
+        x, y, z = (int(v) for v in rng.integers(0, 2 ** 32, size=3))
+        assert hs.hs_xxhash32_three(x, y, z) == oracle_lib.bo_xxhash32_three(x, y, z)
+    a, b = C.c_uint32(12345), C.c_uint32(12345)
+    for _ in range(100):
+        assert hs.hs_lcg(C.byref(a)) == oracle_lib.bo_lcg(C.byref(b)) and a.value == b.value
+    # materials
+    unit = lambda: (lambda v: (v / np.linalg.norm(v)).astype(np.float32))(rng.normal(size=3))
+    for kind, p0, p1 in ((_ffi.BN_MAT_LAMBERTIAN, 0, 0), (_ffi.BN_MAT_MIRROR, 0, 0), (_ffi.BN_MAT_DIELECTRIC, 1.5, 0), (_ffi.BN_MAT_DIELECTRIC, 1.1, 0),
+                         (_ffi.BN_MAT_PBR, 0.0, 0.16), (_ffi.BN_MAT_PBR, 1.0, 0.0025), (_ffi.BN_MAT_PBR, 0.5, 1.0)):
+        m = _ffi.BnMaterial()
+        m.type, m.p0, m.p1 = kind, p0, p1
+        m.base_color[:] = [0.8, 0.5, 0.3]
+        for _ in range(300):
+            wo, wi, u = unit(), unit(), rng.random(3, dtype=np.float32)
+            got = np.zeros(4, np.float32)
+            hs.hs_material_eval(C.addressof(m), wo.ctypes.data, wi.ctypes.data, got.ctypes.data)
+            assert np.array_equal(got.view(np.uint32), oracle_ffi.material_eval(m, wo, wi).view(np.uint32))
+            got = np.zeros(7, np.float32)
+            hs.hs_material_sample(C.addressof(m), wo.ctypes.data, float(u[0]), u[1:].ctypes.data, got.ctypes.data)
+            assert np.array_equal(got.view(np.uint32), oracle_ffi.material_sample(m, wo, float(u[0]), u[1:]).view(np.uint32))
+    # camera + light sampler over whole scenes
+    for name in ("cbox_pt", "material_sweep"):
+        scene = scene_loader(name)
+        oracle, host = OracleScene(scene.desc), HostScene(hs, scene)
+        for _ in range(300):
+            x, y = int(rng.integers(0, 64)), int(rng.integers(0, 48))
+            u = rng.random(4, dtype=np.float32)
+            got = np.zeros(1, dtype=RAY_DTYPE)
+            hs.hs_camera_ray(host.h, 64, 48, x, y, u.ctypes.data, got.ctypes.data)
+            want = oracle.camera_ray(64, 48, x, y, u[:2], u[2:])
+            assert got.tobytes() == want.tobytes()
+            p = rng.uniform(-50, 150, size=3).astype(np.float32)
+            ul = rng.random(3, dtype=np.float32)
+            got = np.zeros(10, np.float32)
+            hs.hs_light_sample(host.h, p.ctypes.data, float(ul[0]), ul[1:].ctypes.data, got.ctypes.data)
+            assert np.array_equal(got.view(np.uint32), oracle.light_sample(p, float(ul[0]), ul[1:]).view(np.uint32))
