@@ -44,7 +44,12 @@ BN_DEV float div_ieee(float a, float s) {
 #ifdef BN_EXP_SHARED_RCP
 // experiment queued for the next GPU session (default off): the three divisions of a normalize() share one correctly
 // rounded reciprocal (include/bn_portable_math.h: bn_div_by_rcp — same bits as the IEEE division on the guarded domain)
-static __device__ __noinline__ float3 div3_ieee(float3 a, float s) { return f3(div_ieee(a.x, s), div_ieee(a.y, s), div_ieee(a.z, s)); }  // one cold copy
+#ifdef BN_HOSTSIM
+#define BN_NOINLINE_DEV static __attribute__((noinline))
+#else
+#define BN_NOINLINE_DEV static __device__ __noinline__
+#endif
+BN_NOINLINE_DEV float3 div3_ieee(float3 a, float s) { return f3(div_ieee(a.x, s), div_ieee(a.y, s), div_ieee(a.z, s)); }  // one cold copy
 BN_DEV float3 operator/(float3 a, float s) {
   const bool ok = bn_div_rcp_ok(s) && (a.x == 0.f || bn_div_rcp_ok(a.x)) && (a.y == 0.f || bn_div_rcp_ok(a.y)) && (a.z == 0.f || bn_div_rcp_ok(a.z));
   if (!ok) return div3_ieee(a, s);

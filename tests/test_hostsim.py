@@ -24,18 +24,17 @@ from test_oracle_bruteforce import _random_scene_json
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def hs(root):
+def _build_hostsim(root, tag="", defines=()):
     src = os.path.join(HERE, "hostsim")
     out_dir = os.path.join(src, "_build")
     os.makedirs(out_dir, exist_ok=True)
-    lib_path = os.path.join(out_dir, "libhostsim.so")
+    lib_path = os.path.join(out_dir, f"libhostsim{tag}.so")
     csrc = os.path.join(root, "barnacle_b200", "csrc", "cuda")
     deps = [os.path.join(src, f) for f in ("hostsim.cpp", "device_shim.h")] + \
            [os.path.join(csrc, f) for f in ("traverse.cuh", "shade.cuh", "vecmath.cuh", "device_scene.h", "scene_convert.cpp", "scene_convert.h", "traverse_limits.h")] + \
            [os.path.join(root, "include", "bn_portable_math.h")]
     if not os.path.exists(lib_path) or any(os.path.getmtime(d) > os.path.getmtime(lib_path) for d in deps):
-        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include", *["-D" + d for d in defines],
                         os.path.join(src, "hostsim.cpp"), os.path.join(csrc, "scene_convert.cpp"), "-o", lib_path], check=True)
     lib = C.CDLL(lib_path)
     lib.hs_scene_create.restype = C.c_void_p
@@ -52,6 +51,17 @@ def hs(root):
     lib.hs_lcg.restype = C.c_float
     lib.hs_lcg.argtypes = [C.POINTER(C.c_uint32)]
     return lib
+
+
+@pytest.fixture(scope="module")
+def hs(root):
+    return _build_hostsim(root)
+
+
+@pytest.fixture(scope="module")
+def hs_shared_rcp(root):
+    """The same functions built with the default-off shade experiment -DBN_EXP_SHARED_RCP (vecmath.cuh)."""
+    return _build_hostsim(root, "_shared_rcp", ["BN_EXP_SHARED_RCP"])
 
 
 class HostScene:
@@ -147,6 +157,12 @@ def test_device_traversal_on_randomised_scenes(hs, lib, seed, n_instances):
     want = oracle.trace(adv)
     for mode in (0, 1):
         _same_hits(desc, host.trace(adv, mode=mode)[0], want)
+
+
+def test_shared_reciprocal_experiment_keeps_the_shading_functions_bit_identical(hs_shared_rcp, scene_loader, oracle_lib):
+    """normalize() through one shared reciprocal: every vector division in the camera, material and
+    light-sampler functions goes through it, and every result keeps its bits."""
+    test_device_shading_functions_on_the_host_equal_the_oracle(hs_shared_rcp, scene_loader, oracle_lib)
 
 
 def test_device_shading_functions_on_the_host_equal_the_oracle(hs, scene_loader, oracle_lib):
