@@ -190,108 +190,8 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
     float sh_tmax = 0.f;
     if (i < n) {
       const float4 a = s0[i], b = s1[i], c = s2[i], h = hits[i];
-      const float3 o = f3(a.x, a.y, a.z), d = f3(a.w, b.x, b.y);
-      beta = f3(b.z, b.w, c.x);
-      const float prev_pdf = c.y;
-      rng = __float_as_uint(c.z);
-      pid = __float_as_int(c.w);
-      const float t = h.x;
-      const int inst = __float_as_int(h.y), prim = __float_as_int(h.z);
-      if (inst >= 0) {
-        const float4* hp = reinterpret_cast<const float4*>(sc.inst_head + inst);
-        const float4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
-        const uint32_t kind_prim = __float_as_uint(h0.w);
-        const int material = __float_as_int(h1.w), light = __float_as_int(h2.x);
-        const Mat43 W2O = load_mat43(reinterpret_cast<const float4*>(sc.inst_w2o + inst));
-        const Mat43 O2W = load_mat43(reinterpret_cast<const float4*>(sc.inst_o2w + inst));
-        // rebuild the interaction exactly as the intersection routines produced it
-        const float3 oo = transform_point(o, W2O), od = transform_dir(d, W2O);
-        const float3 pobj = point_at(oo, od, t);
-        float3 nobj;
-        const bool is_sphere = (kind_prim & 0x80000000u) != 0u;
-        if (is_sphere) {  // Sphere.fs:50-62 / 64-75 (normal flipped on the near root only)
-          nobj = normalize(pobj);
-          if (prim == 0 && dot(nobj, od) > 0.f) nobj = -nobj;
-        } else {          // Mesh.fs:76-78
-          float3 p0, p1, p2;
-          load_tri(sc.tris + prim, p0, p1, p2);  // prim is the scene-wide triangle index
-          nobj = normalize(cross(p1 - p0, p2 - p0));
-        }
-        // LocalGeometry.Transform (Primitive.fs:57-58)
-        P = transform_point(pobj, O2W);
-        const Onb onb = transform_onb(onb_from_n(nobj), O2W);
-
-        if (wp.integrator == BN_INTEGRATOR_NORMAL) {  // NormalIntegrator.Li (Normal.fs:10-17)
-          const float3 c = 0.5f * (onb.n + splat(1.f));
-          rad[pid] = make_float4(c.x, c.y, c.z, 0.f);
-        } else if (wp.integrator == BN_INTEGRATOR_DIRECT && bounce == 0) {
-          if (light >= 0) {  // Direct.fs:16-17: L + EvalEmit(-ray.Direction)
-            const float3 Le = light_eval(load_light(sc, light), dot(-d, onb.n));
-            const float4 L4 = rad[pid];
-            rad[pid] = make_float4(L4.x + Le.x, L4.y + Le.y, L4.z + Le.z, 0.f);
-          }
-        } else if (light >= 0) {  // PathTracing.fs:30-40 + UniformLightSampler.Eval (Uniform.fs:40-49)
-          const float3 wo = normalize(o - P);
-          const float cos_wo = dot(onb.n, wo);
-          float pdf_surface;
-          if (is_sphere) {  // SphereInstance.EvalPDF, Sphere.fs:115-126
-            const float radius = h2.y;
-            const float j = length(cross(transform_dir(onb.t, W2O), transform_dir(onb.b, W2O)));
-            pdf_surface = j / (4.f * kPi * radius * radius);
-          } else {          // MeshInstance.EvalPDF with tag = 0 (Mesh.fs:300-304), host-precomputed
-            pdf_surface = h2.y;
-          }
-          const float dist2 = length_sq(o - P);
-          const float3 Le = light_eval(load_light(sc, light), dot(wo, onb.n));
-          const float lpdf = dist2 * pdf_surface / (net_max(fabsf(cos_wo), 1e-6f) * (float)sc.n_light_inst);
-          // PathTracing.fs:33-38 MIS weight | Direct.fs:36-38: bsdf * L * (1 / lightPdf), no MIS
-          const float w = wp.integrator == BN_INTEGRATOR_DIRECT ? (1.f / lpdf) : (bounce == 0 ? 1.f : prev_pdf * (1.f / (lpdf + prev_pdf)));
-          const float4 L4 = rad[pid];
-          const float3 L = vfma(beta, Le * w, f3(L4.x, L4.y, L4.z));
-          rad[pid] = make_float4(L.x, L.y, L.z, 0.f);
-        }
-        const bool scatter = wp.integrator == BN_INTEGRATOR_PATH_TRACING || (wp.integrator == BN_INTEGRATOR_DIRECT && bounce == 0);
-        if (material >= 0 && scatter) {
-          const bool direct = wp.integrator == BN_INTEGRATOR_DIRECT;
-          const GMaterial mat = load_material(sc, material);
-          const float usel = lcg(rng);
-          const float ulx = lcg(rng), uly = lcg(rng);
-          const LightSampleRec ls = light_sampler_sample(sc, P, usel, ulx, uly);  // PathTracing.fs:43
-          const float dist = length(ls.p - P);
-          const float3 wo_l = world_to_local(onb, -d);
-          if (direct || ls.pdf != 0.f) {  // PathTracing.fs:47-59 | Direct.fs:25-29 traces whatever the pdf
-            ref_shadow = true;
-            const BsdfEval fe = material_eval(mat, wo_l, world_to_local(onb, ls.wi));
-            sh_a = direct ? fe.bsdf : beta * fe.bsdf;
-            sh_b = ls.L * (1.f / (direct ? ls.pdf : fe.pdf + ls.pdf));
-            // fma(0, finite, L) == L bit for bit: the connection cannot change the image
-            const bool null_contrib = sh_a.x == 0.f && sh_a.y == 0.f && sh_a.z == 0.f && isfinite(sh_b.x) && isfinite(sh_b.y) && isfinite(sh_b.z);
-            has_shadow = !null_contrib || (wp.flags & BN_RENDER_TRACE_NULL_SHADOW);
-            sh_wi = ls.wi;
-            sh_tmax = dist - 1e-3f;
-          }
-          const float ulobe = lcg(rng);
-          const float ubx = lcg(rng), uby = lcg(rng);
-          const BsdfSample bs = material_sample(mat, wo_l, ulobe, ubx, uby);  // :61
-          if (direct) {  // Direct.fs:31-38: the sampled direction is followed whatever its pdf; its weight is bsdf alone
-            nd = local_to_world(onb, bs.wi);
-            beta = bs.eval.bsdf;
-            bs_pdf = bs.eval.pdf;
-            alive = true;
-          } else if (bs.eval.pdf != 0.f) {
-            nd = local_to_world(onb, bs.wi);
-            beta = beta * bs.eval.bsdf * (1.f / bs.eval.pdf);
-            bs_pdf = bs.eval.pdf;
-            bool cont = true;
-            if (bounce >= wp.rr_depth) {  // :69-75
-              const float q = net_min(1.f, net_max(beta.x, net_max(beta.y, beta.z)));
-              if (lcg(rng) < q) beta = beta * (1.f / q);
-              else cont = false;
-            }
-            alive = cont && (bounce + 1 < wp.max_depth);
-          }
-        }
-      }
+      shade_lane(sc, wp.integrator, wp.rr_depth, wp.max_depth, wp.flags, bounce, a, b, c, h, rad, alive, has_shadow, ref_shadow, P, nd, beta, bs_pdf, rng, pid,
+                 sh_wi, sh_a, sh_b, sh_tmax);
     }
     const int pos = warp_append(n_out, alive);
     if (alive) {

@@ -106,6 +106,80 @@ void hs_light_sample(void* h, const float* p, float usel, const float* ul, float
   out[0] = r.p.x; out[1] = r.p.y; out[2] = r.p.z; out[3] = r.L.x; out[4] = r.L.y; out[5] = r.L.z; out[6] = r.pdf;
   out[7] = r.wi.x; out[8] = r.wi.y; out[9] = r.wi.z;
 }
+// One camera path through the kernels' device functions, in the order the wavefront runs them for that path:
+// raygen (k_raygen's body, restated: four draws, primary_ray) -> per bounce: extend (trace_lane_impl, fast form with the
+// exact form as fallback = phases + fix-up kernel) -> shade_lane (the shade kernel's lane body, shade.cuh) -> shadow ray
+// (any hit) + connect (ShadowIO::store: one fma).  Returns the path's radiance; rays[0] / rays[1] count extend / shadow rays.
+static float3 hs_path(const bn::DScene& sc, const BnRenderParams& p, int x, int y, int sample, uint64_t* rays) {
+  uint32_t rng = bn::xxhash32_three((uint32_t)x, (uint32_t)y, (uint32_t)(p.frame_id * p.spp + sample));
+  const float upx = bn::lcg(rng), upy = bn::lcg(rng);
+  const float ulx = bn::lcg(rng), uly = bn::lcg(rng);
+  float3 o, d;
+  bn::primary_ray(sc.cam, p.width, p.height, x, y, upx, upy, ulx, uly, o, d);
+  float4 rad = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a = make_float4(o.x, o.y, o.z, d.x), b = make_float4(d.y, d.z, 1.f, 1.f), c = make_float4(1.f, 0.f, __uint_as_float(rng), __int_as_float(0));
+  const int n_bounces = p.integrator == BN_INTEGRATOR_PATH_TRACING ? p.max_depth : (p.integrator == BN_INTEGRATOR_DIRECT ? 2 : 1);
+  auto trace = [&](bool any, float3 ro, float3 rd, float tmax) {
+    bn::TraceResult r;
+    bool done = false;
+    if (sc.all_finite != 0u && bn::slab_fast_ok(ro, bn::rcp3(rd)))
+      done = any ? bn::trace_lane_impl<true, true>(sc, ro, rd, tmax, r) : bn::trace_lane_impl<false, true>(sc, ro, rd, tmax, r);
+    if (!done) {
+      if (any) bn::trace_lane_impl<true, false>(sc, ro, rd, tmax, r);
+      else bn::trace_lane_impl<false, false>(sc, ro, rd, tmax, r);
+    }
+    return r;
+  };
+  for (int bounce = 0; bounce < n_bounces; ++bounce) {
+    const bn::TraceResult hit = trace(false, bn::f3(a.x, a.y, a.z), bn::f3(a.w, b.x, b.y), INFINITY);
+    rays[0]++;
+    const float4 h = make_float4(hit.t, __int_as_float(hit.inst), __int_as_float(hit.prim), 0.f);  // ExtendIO::store
+    bool alive = false, has_shadow = false, ref_shadow = false;
+    float3 P = bn::splat(0.f), nd = bn::splat(0.f), beta = bn::splat(0.f), sh_wi = bn::splat(0.f), sh_a = bn::splat(0.f), sh_b = bn::splat(0.f);
+    float bs_pdf = 0.f, sh_tmax = 0.f;
+    uint32_t rng2 = 0;
+    int pid = 0;
+    bn::shade_lane(sc, p.integrator, p.rr_depth, p.max_depth, p.flags, bounce, a, b, c, h, &rad, alive, has_shadow, ref_shadow, P, nd, beta, bs_pdf, rng2, pid,
+                   sh_wi, sh_a, sh_b, sh_tmax);
+    if (has_shadow) {
+      rays[1]++;
+      if (!trace(true, P, sh_wi, sh_tmax).hit) {  // ShadowIO::store
+        const float3 L = bn::vfma(sh_a, sh_b, bn::f3(rad.x, rad.y, rad.z));
+        rad = make_float4(L.x, L.y, L.z, 0.f);
+      }
+    }
+    if (!alive) break;
+    a = make_float4(P.x, P.y, P.z, nd.x); b = make_float4(nd.y, nd.z, beta.x, beta.y); c = make_float4(beta.z, bs_pdf, __uint_as_float(rng2), __int_as_float(0));
+  }
+  return bn::f3(rad.x, rad.y, rad.z);
+}
+
+// radiance: [sample][y][x][3] over the full image (bn_render_radiance's layout); film (may be NULL): Film.Pixels layout,
+// accumulated like k_accumulate (fma(1/spp, L, acc) over sampleId ascending).  stats (may be NULL): extend, shadow rays.
+int hs_render(void* h, const BnRenderParams* p, float* radiance, float* film, uint64_t* stats) {
+  const bn::DScene& sc = static_cast<HsScene*>(h)->d;
+  uint64_t rays[2] = {0, 0};
+  const float inv_spp = 1.f / (float)p->spp;
+  for (int y = 0; y < p->height; ++y)
+    for (int x = 0; x < p->width; ++x) {
+      float3 acc = bn::splat(0.f);
+      for (int s = 0; s < p->spp; ++s) {
+        const float3 L = hs_path(sc, *p, x, y, s, rays);
+        if (radiance) {
+          float* o = radiance + (((size_t)s * p->height + y) * p->width + x) * 3;
+          o[0] = L.x; o[1] = L.y; o[2] = L.z;
+        }
+        acc = bn::vfma(bn::splat(inv_spp), bn::operator*(L, 1.f / 1.f), acc);  // * rcp(camera pdf), pdf == 1 (k_accumulate)
+      }
+      if (film) {
+        float* px = film + ((size_t)(p->height - y - 1) * p->width + x) * 3;
+        px[0] = acc.x; px[1] = acc.y; px[2] = acc.z;
+      }
+    }
+  if (stats) { stats[0] = rays[0]; stats[1] = rays[1]; }
+  return 0;
+}
+
 uint32_t hs_xxhash32_three(uint32_t x, uint32_t y, uint32_t z) { return bn::xxhash32_three(x, y, z); }
 float hs_lcg(uint32_t* state) { return bn::lcg(*state); }
 

@@ -46,6 +46,7 @@ def _build_hostsim(root, tag="", defines=()):
     lib.hs_material_eval.argtypes = [C.c_void_p] * 4
     lib.hs_material_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
     lib.hs_light_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    lib.hs_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_xxhash32_three.restype = C.c_uint32
     lib.hs_xxhash32_three.argtypes = [C.c_uint32] * 3
     lib.hs_lcg.restype = C.c_float
@@ -76,6 +77,14 @@ class HostScene:
         fast = C.c_uint64(0)
         assert self.hs.hs_trace(self.h, rays.ctypes.data, len(rays), 1 if any_hit else 0, mode, hits.ctypes.data, C.byref(fast)) == 0
         return hits, fast.value
+
+    def render(self, params):
+        """(radiance [spp, h, w, 3], film [h*w, 3], extend rays, shadow rays) through the kernels' device functions."""
+        rad = np.zeros((params.spp, params.height, params.width, 3), dtype=np.float32)
+        film = np.zeros((params.height * params.width, 3), dtype=np.float32)
+        st = np.zeros(2, dtype=np.uint64)
+        assert self.hs.hs_render(self.h, C.byref(params), rad.ctypes.data, film.ctypes.data, st.ctypes.data) == 0
+        return rad, film, int(st[0]), int(st[1])
 
     def __del__(self):
         self.hs.hs_scene_destroy(self.h)
@@ -206,3 +215,33 @@ def test_device_shading_functions_on_the_host_equal_the_oracle(hs, scene_loader,
             got = np.zeros(10, np.float32)
             hs.hs_light_sample(host.h, p.ctypes.data, float(ul[0]), ul[1:].ctypes.data, got.ctypes.data)
             assert np.array_equal(got.view(np.uint32), oracle.light_sample(p, float(ul[0]), ul[1:]).view(np.uint32))
+
+
+def _bits_equal(a, b):
+    return ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all()
+
+
+@pytest.mark.parametrize("name,w,h,spp,max_depth,rr_depth", [("cbox_pt", 40, 40, 3, 8, 5), ("material_sweep", 48, 27, 3, 8, 2), ("cbox_bunny", 32, 32, 2, 6, 3),
+                                                       ("bunny_instanced_small", 32, 18, 2, 5, 5)])
+def test_whole_paths_through_the_device_functions_equal_the_oracle(hs, scene_loader, oracle_lib, name, w, h, spp, max_depth, rr_depth):
+    """raygen -> (extend -> shade_lane -> shadow + connect) x bounces -> accumulate, with the kernels' own device code on the
+    host: per-path radiance, film and ray counts are the oracle's, bit for bit."""
+    oracle_ffi.set_portable_math(True)
+    scene = scene_loader(name)
+    oracle, host = OracleScene(scene.desc), HostScene(hs, scene)
+    for integrator in (_ffi.BN_INTEGRATOR_PATH_TRACING, _ffi.BN_INTEGRATOR_DIRECT, _ffi.BN_INTEGRATOR_NORMAL):
+        p = make_params(w, h, spp, max_depth=max_depth, rr_depth=rr_depth, integrator=integrator)
+        rad, film, n_ext, n_sh = host.render(p)
+        assert _bits_equal(rad, oracle.render_radiance(p, threads=1))
+        want_film, st = oracle.render(p, threads=1, counters=True)           # instrumented: also counts the non-null NEE rays
+        assert _bits_equal(film, want_film)
+        assert np.nan_to_num(film).any()
+        if integrator == _ffi.BN_INTEGRATOR_PATH_TRACING:
+            assert n_ext == st["extend_rays"] and n_sh == st["shadow_rays_nonnull"]   # null-contribution NEE rays are not traced
+
+
+def test_shared_reciprocal_experiment_keeps_whole_paths_bit_identical(hs_shared_rcp, scene_loader, oracle_lib):
+    """DESIGN.md §8 item 5 at the level of the image: every normalize() of the shading code through the shared reciprocal,
+    same film."""
+    for name, w, h, spp in (("cbox_pt", 40, 40, 3), ("material_sweep", 48, 27, 3)):
+        test_whole_paths_through_the_device_functions_equal_the_oracle(hs_shared_rcp, scene_loader, oracle_lib, name, w, h, spp, 8, 3)
