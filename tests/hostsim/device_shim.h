@@ -26,11 +26,31 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
-// warp-level primitives: only named inside traverse_persistent(), which the host never instantiates; they have to parse
+// ---- warp-level primitives -----------------------------------------------------------------------------------
+// Plain builds: trivial one-lane definitions (traverse_persistent is never instantiated, they only have to parse).
+// With BN_HOSTSIM_WARP (warp_emulator.h) they are rendezvous points of 32 lanes that run as fibers in lock step, and
+// threadIdx.x reads the running lane's id: the warp-synchronous traversal loop then runs on the host as it is written.
+#ifdef BN_HOSTSIM_WARP
+unsigned hostsim_warp_sync(int kind, unsigned value, int src_lane);  // 0 REDUX.SUM, 1 ballot, 2 shuffle
+unsigned hostsim_lane_id(void);
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return hostsim_warp_sync(0, v, 0); }
+static inline unsigned __ballot_sync(unsigned, int p) { return hostsim_warp_sync(1, p ? 1u : 0u, 0); }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)hostsim_warp_sync(2, (unsigned)v, src); }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return hostsim_warp_sync(2, v, src); }
+static inline float __shfl_sync(unsigned, float v, int src) { return __uint_as_float(hostsim_warp_sync(2, __float_as_uint(v), src)); }
+struct HostsimLaneX { operator unsigned() const { return hostsim_lane_id(); } };
+struct HostsimThreadIdx { HostsimLaneX x; unsigned y = 0, z = 0; };
+static HostsimThreadIdx threadIdx;
+#else
 static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
-static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+struct HostsimThreadIdx { unsigned x = 0, y = 0, z = 0; };
+static HostsimThreadIdx threadIdx;
+#endif
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }  // lanes are fibers of one thread: no race
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
-struct HostsimDim { unsigned x = 0, y = 0, z = 0; };
-static HostsimDim threadIdx, blockIdx, blockDim, gridDim;
+struct HostsimDim { unsigned x = 1, y = 1, z = 1; };
+static HostsimDim blockDim, gridDim;
+struct HostsimBlockIdx { unsigned x = 0, y = 0, z = 0; };
+static HostsimBlockIdx blockIdx;

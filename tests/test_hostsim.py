@@ -245,3 +245,94 @@ def test_shared_reciprocal_experiment_keeps_whole_paths_bit_identical(hs_shared_
     same film."""
     for name, w, h, spp in (("cbox_pt", 40, 40, 3), ("material_sweep", 48, 27, 3)):
         test_whole_paths_through_the_device_functions_equal_the_oracle(hs_shared_rcp, scene_loader, oracle_lib, name, w, h, spp, 8, 3)
+
+
+# ---- the warp-synchronous persistent loop itself, on an emulated warp (tests/hostsim/warp_emulator.cpp) ----------------
+def _build_warp_emulator(root, tag="", defines=()):
+    src = os.path.join(HERE, "hostsim")
+    out_dir = os.path.join(src, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    lib_path = os.path.join(out_dir, f"libwarp{tag}.so")
+    csrc = os.path.join(root, "barnacle_b200", "csrc", "cuda")
+    deps = [os.path.join(src, f) for f in ("warp_emulator.cpp", "device_shim.h")] + \
+           [os.path.join(csrc, f) for f in ("traverse.cuh", "vecmath.cuh", "device_scene.h", "scene_convert.cpp", "scene_convert.h", "traverse_limits.h")]
+    if not os.path.exists(lib_path) or any(os.path.getmtime(d) > os.path.getmtime(lib_path) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include", *["-D" + d for d in defines],
+                        os.path.join(src, "warp_emulator.cpp"), os.path.join(csrc, "scene_convert.cpp"), "-o", lib_path], check=True)
+    lib = C.CDLL(lib_path)
+    lib.hsw_scene_create.restype = C.c_void_p
+    lib.hsw_scene_create.argtypes = [C.c_void_p, C.c_int]
+    lib.hsw_scene_destroy.argtypes = [C.c_void_p]
+    lib.hsw_has_flat_tlas.argtypes = [C.c_void_p]
+    lib.hsw_last_error.restype = C.c_char_p
+    lib.hsw_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def warp(root):
+    return _build_warp_emulator(root)
+
+
+@pytest.fixture(scope="module")
+def warp_any_unordered(root):
+    """The same loop built with the default-off experiment -DBN_EXP_ANY_UNORDERED."""
+    return _build_warp_emulator(root, "_any_unordered", ["BN_EXP_ANY_UNORDERED"])
+
+
+def _warp_trace(lib, scene, rays, any_hit, flat=True):
+    h = lib.hsw_scene_create(C.cast(scene.desc, C.c_void_p), 1 if flat else 0)
+    assert h, lib.hsw_last_error()
+    try:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        st = np.zeros(2, dtype=np.uint64)
+        assert lib.hsw_trace(h, rays.ctypes.data, len(rays), 1 if any_hit else 0, hits.ctypes.data, st.ctypes.data) == 0, lib.hsw_last_error()
+        return hits, int(st[0]), int(st[1]), bool(lib.hsw_has_flat_tlas(h))
+    finally:
+        lib.hsw_scene_destroy(h)
+
+
+def _check_persistent_loop(lib, scene, n_random, seed, flat=True):
+    desc = scene.desc.contents
+    oracle = OracleScene(scene.desc)
+    batches = [("primary", oracle.primary_rays(make_params(32, 24, 1))), ("random", random_rays(scene, n_random, seed=seed)),
+               ("adversarial", _adversarial(scene, n_random // 2, seed=seed + 1)), ("short", random_rays(scene, 37, seed=seed + 2)),
+               ("empty", random_rays(scene, 0, seed=0))]
+    used_flat = False
+    for label, rays in batches:
+        want = oracle.trace(rays)
+        got, rendezvous, deferred, used_flat = _warp_trace(lib, scene, rays, False, flat)
+        _same_hits(desc, got, want)
+        if label == "adversarial":
+            assert deferred > 0                                            # the NaN-lane rays went through the exact path
+        if len(rays):
+            assert rendezvous > 0
+        tm = rays.copy()
+        tm["tmax"] = np.where(want["instance"] >= 0, want["t"] * np.float32(1.5), np.float32(50.0))
+        tm["tmax"][::2] = np.where(want["instance"][::2] >= 0, want["t"][::2] * np.float32(0.5), np.float32(5.0))
+        got_any = _warp_trace(lib, scene, tm, True, flat)[0]["instance"]
+        assert np.array_equal(got_any, oracle.trace(tm, any_hit=True)["instance"])
+    return used_flat
+
+
+@pytest.mark.parametrize("name,flat", [("cbox_pt", True), ("cbox_pt", False), ("cbox_bunny", True), ("material_sweep", True), ("bunny_instanced_small", True)])
+def test_persistent_traversal_loop_on_an_emulated_warp_equals_the_oracle(warp, scene_loader, name, flat):
+    """traverse_persistent as written — phase votes, stay loops, refill, small-TLAS scan (the two Cornell-box scenes; also with
+    the scan switched off), identity-instance shortcut, deferral — run by 32 fibers in lock step: same hits as the oracle."""
+    used_flat = _check_persistent_loop(warp, scene_loader(name), 3000, seed=41, flat=flat)
+    assert used_flat == (flat and name in ("cbox_pt", "cbox_bunny"))
+
+
+@pytest.mark.parametrize("seed,n_instances", [(51, 3), (52, 16), (53, 17), (54, 120)])
+def test_persistent_traversal_loop_on_randomised_scenes(warp, lib, seed, n_instances):
+    rng = np.random.default_rng(seed)
+    _check_persistent_loop(warp, Scene.LoadString(_random_scene_json(rng, n_instances)), 2000, seed=seed)
+
+
+def test_unordered_any_hit_experiment_gives_the_same_answers(warp_any_unordered, scene_loader, lib):
+    """-DBN_EXP_ANY_UNORDERED: shadow rays walk left-first whatever the ray direction; occlusion answers (and, untouched,
+    the closest hits) stay the oracle's."""
+    for name in ("cbox_bunny", "material_sweep", "bunny_instanced_small"):
+        _check_persistent_loop(warp_any_unordered, scene_loader(name), 2500, seed=61)
+    _check_persistent_loop(warp_any_unordered, Scene.LoadString(_random_scene_json(np.random.default_rng(62), 40)), 2000, seed=62)
