@@ -187,4 +187,12 @@ int hsw_trace(void* h, const BnRay* rays, uint64_t n, int any_hit, BnHit* hits, 
   return 0;
 }
 
+#ifdef BN_TRAV_STATS
+// phase statistics of the emulated warp (tools/warp_stats.py): [any * 10 + k] = executions of phase k (0 N, 1 T, 2 E,
+// 3 all phases, 4 S), [any * 10 + 5 + k] = lanes that were ready in them — the counters the --stats GPU build keeps
+void hsw_stats(unsigned long long* out, int reset) {
+  for (int k = 0; k < 24; ++k) { out[k] = bn::g_trav_stats[k]; if (reset) bn::g_trav_stats[k] = 0; }
+}
+#endif
+
 }  // extern "C"
