@@ -414,6 +414,11 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
           }
         }
         if (__popc(__ballot_sync(kFull, (int)cur >= 0)) < kStayMin) break;
+#ifdef BN_EXP_STAY_REFILL
+        // experiment queued for the next GPU session (default off): closest-hit rays in tree-TLAS scenes leave
+        // the stay loop as soon as a refill is due (BN_EXP_STAY_REFILL idle lanes), instead of stepping on with those lanes empty
+        if (!ANY && !flat && !exhausted && __popc(__ballot_sync(kFull, cur == kNone)) >= BN_EXP_STAY_REFILL) break;
+#endif
       }
     } else if (nT >= nE && nT >= nS) {
       // ---- phase T: next triangle of the held BLAS leaf (slot order), behind its own
@@ -443,6 +448,9 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
           }
         }
         if (__popc(__ballot_sync(kFull, (cur >> 30) == 2u)) < kStayT) break;
+#ifdef BN_EXP_STAY_REFILL
+        if (!ANY && !flat && !exhausted && __popc(__ballot_sync(kFull, cur == kNone)) >= BN_EXP_STAY_REFILL) break;
+#endif
       }
     } else if (nE >= nS) {
       // ---- phase E: PrimitiveInstance.Intersect (Primitive.fs:111-129); the world AABB

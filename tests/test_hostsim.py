@@ -169,7 +169,7 @@ def test_device_traversal_on_randomised_scenes(hs, lib, seed, n_instances):
 
 
 def test_shared_reciprocal_experiment_keeps_the_shading_functions_bit_identical(hs_shared_rcp, scene_loader, oracle_lib):
-    """normalize() through one shared reciprocal (DESIGN.md §8 item 5): every vector division in the camera, material and
+    """normalize() through one shared reciprocal (DESIGN.md §8 item 6): every vector division in the camera, material and
     light-sampler functions goes through it, and every result keeps its bits."""
     test_device_shading_functions_on_the_host_equal_the_oracle(hs_shared_rcp, scene_loader, oracle_lib)
 
@@ -241,7 +241,7 @@ def test_whole_paths_through_the_device_functions_equal_the_oracle(hs, scene_loa
 
 
 def test_shared_reciprocal_experiment_keeps_whole_paths_bit_identical(hs_shared_rcp, scene_loader, oracle_lib):
-    """DESIGN.md §8 item 5 at the level of the image: every normalize() of the shading code through the shared reciprocal,
+    """DESIGN.md §8 item 6 at the level of the image: every normalize() of the shading code through the shared reciprocal,
     same film."""
     for name, w, h, spp in (("cbox_pt", 40, 40, 3), ("material_sweep", 48, 27, 3)):
         test_whole_paths_through_the_device_functions_equal_the_oracle(hs_shared_rcp, scene_loader, oracle_lib, name, w, h, spp, 8, 3)
@@ -336,3 +336,10 @@ def test_unordered_any_hit_experiment_gives_the_same_answers(warp_any_unordered,
     for name in ("cbox_bunny", "material_sweep", "bunny_instanced_small"):
         _check_persistent_loop(warp_any_unordered, scene_loader(name), 2500, seed=61)
     _check_persistent_loop(warp_any_unordered, Scene.LoadString(_random_scene_json(np.random.default_rng(62), 40)), 2000, seed=62)
+
+
+def test_stay_refill_experiment_gives_the_same_hits(root, scene_loader, lib):
+    """-DBN_EXP_STAY_REFILL=14: a different moment to leave the stay loops, the same hits."""
+    variant = _build_warp_emulator(root, "_stay_refill", ["BN_EXP_STAY_REFILL=14"])
+    for name in ("material_sweep", "bunny_instanced_small", "cbox_bunny"):
+        _check_persistent_loop(variant, scene_loader(name), 2500, seed=71)
