@@ -74,6 +74,13 @@ __device__ unsigned long long g_trav_stats[24];
 #else
 #define BN_STAT(slot, lanes) do { } while (0)
 #endif
+// Host warp emulator only (tests/hostsim, tools/warp_stats.py): per-lane work in SASS-instruction units; the emulator
+// charges a warp the MAXIMUM over its lanes between two rendezvous, i.e. what a SIMT machine pays for a divergent step.
+#if defined(BN_TRAV_STATS) && defined(BN_HOSTSIM_WARP)
+#define BN_WORK(units) ::hostsim_work(units)  /* declared by tests/hostsim/device_shim.h */
+#else
+#define BN_WORK(units) do { } while (0)
+#endif
 
 BN_DEV uint32_t fbits(float f) { return __float_as_uint(f); }
 
@@ -344,6 +351,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
         // future window into L2.
         if (mine + kPrefetchAhead < n) io.prefetch(mine + kPrefetchAhead);
         float3 wd;
+        BN_WORK(60);
         io.load(mine, wo, wd, t);
         wdx = wd.x; wdy = wd.y; wdz = wd.z;
         winv = rcp3(wd);
@@ -361,6 +369,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
           const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns & 7u) * n_inst);
           uint32_t mask = 0u;
           for (uint32_t k = 0; k < n_inst; ++k) {
+            BN_WORK(25);
             const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
             if (slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) mask |= 1u << k;
           }
@@ -387,6 +396,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
       for (;;) {
         BN_STAT(0, __popc(__ballot_sync(kFull, (int)cur >= 0)));
         if ((int)cur >= 0) {
+          BN_WORK(75);
           const float4* np = node_base + (size_t)(cur & kIndexMask) * 4u;
           const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
           const Slab sl = slab<true>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv);
@@ -437,6 +447,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
           const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
           float tp, u, v;
           bool done = false;
+          BN_WORK(slab_pass<true>(slab<true>(lo, hi, o, inv), t) ? 95 : 45);
           if (slab_pass<true>(slab<true>(lo, hi, o, inv), t) && tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
             h_inst = cur_inst; h_prim = (int)tri; h_u = u; h_v = v;
             if (ANY) { finish(); done = true; }
@@ -457,6 +468,7 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
       // test already happened (parent node / ordered scan)
       BN_STAT(2, nE);
       if (isE) {
+        BN_WORK(70);
         const uint32_t slot = cur & kIndexMask;
         const float4* ip = reinterpret_cast<const float4*>(sc.inst_trav + slot);
         const float4 m0 = __ldg(ip + 3), m2 = __ldg(ip + 5);
@@ -512,8 +524,36 @@ BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__
         while (tl_pos != 0u) {
           const uint32_t k = (uint32_t)__ffs((int)tl_pos) - 1u;
           tl_pos &= tl_pos - 1u;
+          BN_WORK(30);
           const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
           if (ANY || slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) {
+#ifdef BN_EXP_SCAN_LEAF
+            // experiment queued for the next GPU session (default off; found on the warp emulator): an identity
+            // mesh instance whose whole BLAS is ONE leaf (the Cornell-box walls: two triangles) is tested right here, in slot
+            // order behind each triangle's own box, instead of sending the lane through a phase-T round trip per wall
+            if (fbits(b.w) != kNone && (fbits(b.w) & kLeafBit)) {
+              const uint32_t leaf = fbits(b.w);
+              const uint32_t count = (leaf >> 27) & 7u, first = leaf & kFirstMask;
+              const float3 wd = f3(wdx, wdy, wdz);
+              bool occluded = false;
+              for (uint32_t j = 0; j < count; ++j) {
+                const float4* tp4 = tri_base + (size_t)(first + j) * 3u;
+                const float4 ta = __ldg(tp4), tb = __ldg(tp4 + 1), tc = __ldg(tp4 + 2);
+                const float3 p0 = f3(ta.x, ta.y, ta.z), p1 = f3(tb.x, tb.y, tb.z), p2 = f3(tc.x, tc.y, tc.z);
+                const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
+                const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
+                float tp, u, v;
+                BN_WORK(slab_pass<true>(slab<true>(lo, hi, wo, winv), t) ? 95 : 45);
+                if (slab_pass<true>(slab<true>(lo, hi, wo, winv), t) && tri_test(p0, p1, p2, wo, wd, t, tp, u, v)) {
+                  h_inst = (int)fbits(a.w); h_prim = (int)(first + j); h_u = u; h_v = v;
+                  if (ANY) { occluded = true; break; }
+                  t = tp;
+                }
+              }
+              if (ANY && occluded) { finish(); found = true; break; }
+              continue;  // next candidate of the scan, against the (possibly shorter) t
+            }
+#endif
             if (fbits(b.w) != kNone) {
               // identity mesh instance: what phase E would do (object space == world space, the BLAS
               // root box is this box), done here so that the ray goes straight to its N / T phase

@@ -33,6 +33,7 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 #ifdef BN_HOSTSIM_WARP
 unsigned hostsim_warp_sync(int kind, unsigned value, int src_lane);  // 0 REDUX.SUM, 1 ballot, 2 shuffle
 unsigned hostsim_lane_id(void);
+void hostsim_work(unsigned units);  // BN_WORK (traverse.cuh, BN_TRAV_STATS builds): per-lane work for the SIMT cost model
 static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return hostsim_warp_sync(0, v, 0); }
 static inline unsigned __ballot_sync(unsigned, int p) { return hostsim_warp_sync(1, p ? 1u : 0u, 0); }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)hostsim_warp_sync(2, (unsigned)v, src); }

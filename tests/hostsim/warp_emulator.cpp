@@ -32,6 +32,8 @@ struct Warp {
   int src[kLanes];
   int running = -1;
   uint64_t rendezvous = 0;
+  unsigned work[kLanes] = {};   // BN_WORK units since the last rendezvous, per lane
+  uint64_t simt_cost = 0;       // sum over rendezvous intervals of the maximum over lanes (+ the intrinsic itself)
   std::string error;
 };
 Warp* g_warp = nullptr;
@@ -100,6 +102,11 @@ bool run_warp(Warp& w) {
     for (int l = 1; l < kLanes; ++l)
       if (w.kind[l] != w.kind[0]) { w.error = "lanes wait at different warp intrinsics (divergent *_sync)"; return false; }
     ++w.rendezvous;
+    {
+      unsigned mx = 0;
+      for (int l = 0; l < kLanes; ++l) { if (w.work[l] > mx) mx = w.work[l]; w.work[l] = 0; }
+      w.simt_cost += mx + (w.kind[0] == 0 ? 30u : 6u);  // a vote with its unpacking / a ballot + popc + branch
+    }
     if (w.kind[0] == 0) {
       unsigned s = 0;
       for (int l = 0; l < kLanes; ++l) s += w.in[l];
@@ -116,6 +123,7 @@ bool run_warp(Warp& w) {
 }  // namespace
 
 unsigned hostsim_lane_id(void) { return (unsigned)g_warp->running; }
+void hostsim_work(unsigned units) { g_warp->work[g_warp->running] += units; }
 unsigned hostsim_warp_sync(int kind, unsigned value, int src_lane) {
   Warp& w = *g_warp;
   const int l = w.running;
@@ -150,7 +158,7 @@ void hsw_scene_destroy(void* h) { delete static_cast<HsWarpScene*>(h); }
 int hsw_has_flat_tlas(void* h) { return static_cast<HsWarpScene*>(h)->d.flat_tlas != nullptr; }
 
 // One emulated warp drains the whole batch through traverse_persistent, then the deferred rays go through trace_exact
-// (the fix-up kernel).  out_stats (may be NULL): [0] rendezvous count, [1] deferred rays.
+// (the fix-up kernel).  out_stats (may be NULL, 3 values): rendezvous count, deferred rays, SIMT cost (BN_TRAV_STATS builds).
 int hsw_trace(void* h, const BnRay* rays, uint64_t n, int any_hit, BnHit* hits, uint64_t* out_stats) {
   const bn::DScene& sc = static_cast<HsWarpScene*>(h)->d;
   std::vector<bn::TraceResult> results((size_t)n);
@@ -183,7 +191,7 @@ int hsw_trace(void* h, const BnRay* rays, uint64_t n, int any_hit, BnHit* hits, 
     }
     hits[i] = out;
   }
-  if (out_stats) { out_stats[0] = w.rendezvous; out_stats[1] = deferred.size(); }
+  if (out_stats) { out_stats[0] = w.rendezvous; out_stats[1] = deferred.size(); out_stats[2] = w.simt_cost; }
   return 0;
 }
 

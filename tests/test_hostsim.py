@@ -169,7 +169,7 @@ def test_device_traversal_on_randomised_scenes(hs, lib, seed, n_instances):
 
 
 def test_shared_reciprocal_experiment_keeps_the_shading_functions_bit_identical(hs_shared_rcp, scene_loader, oracle_lib):
-    """normalize() through one shared reciprocal (DESIGN.md §8 item 6): every vector division in the camera, material and
+    """normalize() through one shared reciprocal (DESIGN.md §8 item 7): every vector division in the camera, material and
     light-sampler functions goes through it, and every result keeps its bits."""
     test_device_shading_functions_on_the_host_equal_the_oracle(hs_shared_rcp, scene_loader, oracle_lib)
 
@@ -241,7 +241,7 @@ def test_whole_paths_through_the_device_functions_equal_the_oracle(hs, scene_loa
 
 
 def test_shared_reciprocal_experiment_keeps_whole_paths_bit_identical(hs_shared_rcp, scene_loader, oracle_lib):
-    """DESIGN.md §8 item 6 at the level of the image: every normalize() of the shading code through the shared reciprocal,
+    """DESIGN.md §8 item 7 at the level of the image: every normalize() of the shading code through the shared reciprocal,
     same film."""
     for name, w, h, spp in (("cbox_pt", 40, 40, 3), ("material_sweep", 48, 27, 3)):
         test_whole_paths_through_the_device_functions_equal_the_oracle(hs_shared_rcp, scene_loader, oracle_lib, name, w, h, spp, 8, 3)
@@ -276,7 +276,7 @@ def warp(root):
 
 @pytest.fixture(scope="module")
 def warp_any_unordered(root):
-    """The same loop built with the default-off experiment -DBN_EXP_ANY_UNORDERED (DESIGN.md §8 item 1)."""
+    """The same loop built with the default-off experiment -DBN_EXP_ANY_UNORDERED (DESIGN.md §8 item 3)."""
     return _build_warp_emulator(root, "_any_unordered", ["BN_EXP_ANY_UNORDERED"])
 
 
@@ -286,7 +286,7 @@ def _warp_trace(lib, scene, rays, any_hit, flat=True):
     try:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         hits = np.zeros(len(rays), dtype=HIT_DTYPE)
-        st = np.zeros(2, dtype=np.uint64)
+        st = np.zeros(3, dtype=np.uint64)
         assert lib.hsw_trace(h, rays.ctypes.data, len(rays), 1 if any_hit else 0, hits.ctypes.data, st.ctypes.data) == 0, lib.hsw_last_error()
         return hits, int(st[0]), int(st[1]), bool(lib.hsw_has_flat_tlas(h))
     finally:
@@ -343,3 +343,13 @@ def test_stay_refill_experiment_gives_the_same_hits(root, scene_loader, lib):
     variant = _build_warp_emulator(root, "_stay_refill", ["BN_EXP_STAY_REFILL=14"])
     for name in ("material_sweep", "bunny_instanced_small", "cbox_bunny"):
         _check_persistent_loop(variant, scene_loader(name), 2500, seed=71)
+
+
+def test_scan_leaf_experiment_gives_the_same_hits(root, scene_loader, lib):
+    """-DBN_EXP_SCAN_LEAF: single-leaf identity instances (the Cornell-box walls) tested inside the scan phase —
+    same hits, same any-hit answers, on the two scenes that use the scan and on small randomised scenes (<= 16 instances)."""
+    variant = _build_warp_emulator(root, "_scan_leaf", ["BN_EXP_SCAN_LEAF"])
+    for name in ("cbox_pt", "cbox_bunny"):
+        assert _check_persistent_loop(variant, scene_loader(name), 3000, seed=81)
+    for seed, n in ((82, 5), (83, 15)):
+        _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n)), 2000, seed=seed)

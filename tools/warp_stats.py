@@ -2,7 +2,8 @@
 BN_TRAV_STATS) on the host-side warp emulator of tests/hostsim and prints, per phase, how often it ran and how many lanes were
 ready — for the committed thresholds and for -D variants — on ray batches shaped like a frame's (primary, bounce-1 and shadow
 rays generated with the oracle).  No GPU needed; what it cannot tell is time (use tools/ab.sh on the B200 for that): it
-counts warp-steps, which is what an issue-bound kernel pays for.
+counts warp-steps and a SIMT cost: per-lane work in SASS-instruction units (BN_WORK in traverse.cuh), charged per rendezvous
+interval at the MAXIMUM over the 32 lanes plus the intrinsic — what an issue-bound kernel pays for a divergent step.
 
     python tools/warp_stats.py [scene] [--define BN_STAY_MIN=8 ...]      # several --define groups: one variant each, ';'-separated
 """
@@ -68,7 +69,7 @@ def run(lib, scene, batches):
     for label, rays, any_hit in batches:
         rays = np.ascontiguousarray(rays)
         hits = np.zeros(len(rays), dtype=HIT_DTYPE)
-        st = np.zeros(2, dtype=np.uint64)
+        st = np.zeros(3, dtype=np.uint64)
         lib.hsw_stats(out, 1)
         assert lib.hsw_trace(h, rays.ctypes.data, len(rays), 1 if any_hit else 0, hits.ctypes.data, st.ctypes.data) == 0
         lib.hsw_stats(out, 1)
@@ -81,7 +82,8 @@ def run(lib, scene, batches):
         votes = v[base + 3]
         steps = sum(cnt.values())
         cost = sum(cnt[k] * COST[k] for k in cnt) + votes * COST["vote"]
-        rows.append((label, len(rays), steps, votes, {k: (cnt[k], lanes[k] / max(cnt[k], 1)) for k in cnt}, sum(lanes.values()) / max(steps, 1), cost / max(len(rays), 1)))
+        rows.append((label, len(rays), steps, votes, {k: (cnt[k], lanes[k] / max(cnt[k], 1)) for k in cnt}, sum(lanes.values()) / max(steps, 1), cost / max(len(rays), 1),
+                     int(st[2]) / max(len(rays), 1)))
     return rows
 
 
@@ -100,9 +102,9 @@ def main():
     for tag, defs in variants:
         lib = build(defs, str(abs(hash(tag)) % 10 ** 8))
         print(f"== {tag}")
-        for label, n, steps, votes, per, lanes, cost in run(lib, scene, batches):
+        for label, n, steps, votes, per, lanes, cost, simt in run(lib, scene, batches):
             ph = "  ".join(f"{k} {c / max(n, 1) * 32:.1f}/ray @{l:.1f}" for k, (c, l) in per.items() if c)
-            print(f"  {label:9s} warp-steps*32/ray {steps * 32 / max(n, 1):6.1f}  votes*32/ray {votes * 32 / max(n, 1):5.1f}  lanes/step {lanes:5.2f}  est. warp-instr/ray {cost:6.1f}   [{ph}]")
+            print(f"  {label:9s} warp-steps*32/ray {steps * 32 / max(n, 1):6.1f}  votes*32/ray {votes * 32 / max(n, 1):5.1f}  lanes/step {lanes:5.2f}  SIMT cost/ray {simt:6.1f} (flat model {cost:5.1f})   [{ph}]")
 
 
 if __name__ == "__main__":
