@@ -353,3 +353,18 @@ def test_scan_leaf_experiment_gives_the_same_hits(root, scene_loader, lib):
         assert _check_persistent_loop(variant, scene_loader(name), 3000, seed=81)
     for seed, n in ((82, 5), (83, 15)):
         _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n)), 2000, seed=seed)
+
+
+@pytest.mark.parametrize("seed,n_instances", [(227, 6), (217, 40), (228, 40)])   # the scenes tests/test_zgpu_random_scenes.py renders on the B200
+def test_whole_paths_on_randomised_scenes(hs, lib, oracle_lib, seed, n_instances):
+    """Paths that start inside overlapping triangle soups, graze spheres under non-uniform scale, leave through gaps: the
+    device functions still return the oracle's radiance, film and ray counts."""
+    oracle_ffi.set_portable_math(True)
+    scene = Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n_instances))
+    oracle, host = OracleScene(scene.desc), HostScene(hs, scene)
+    p = make_params(96, 64, 2, max_depth=6, rr_depth=3)
+    rad, film, n_ext, n_sh = host.render(p)
+    assert _bits_equal(rad, oracle.render_radiance(p, threads=1))
+    want_film, st = oracle.render(p, threads=1, counters=True)
+    assert _bits_equal(film, want_film) and (np.nan_to_num(film).sum(axis=1) > 0).mean() > 0.05
+    assert n_ext == st["extend_rays"] and n_sh == st["shadow_rays_nonnull"]
