@@ -355,12 +355,13 @@ def test_scan_leaf_experiment_gives_the_same_hits(root, scene_loader, lib):
         _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n)), 2000, seed=seed)
 
 
-@pytest.mark.parametrize("seed,n_instances", [(227, 6), (217, 40), (228, 40)])   # the scenes tests/test_zgpu_random_scenes.py renders on the B200
-def test_whole_paths_on_randomised_scenes(hs, lib, oracle_lib, seed, n_instances):
+@pytest.mark.parametrize("seed,n_instances,emitters", [(227, 6, "quad"), (217, 40, "quad"), (228, 40, "quad"), (227, 6, "mixed"), (217, 40, "mixed")])   # the scenes tests/test_zgpu_random_scenes.py renders on the B200
+def test_whole_paths_on_randomised_scenes(hs, lib, oracle_lib, seed, n_instances, emitters):
     """Paths that start inside overlapping triangle soups, graze spheres under non-uniform scale, leave through gaps: the
-    device functions still return the oracle's radiance, film and ray counts."""
+    device functions still return the oracle's radiance, film and ray counts ("mixed": with a one-sided sphere emitter and a
+    one-sided quad besides the two-sided quad)."""
     oracle_ffi.set_portable_math(True)
-    scene = Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n_instances))
+    scene = Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n_instances, emitters))
     oracle, host = OracleScene(scene.desc), HostScene(hs, scene)
     p = make_params(96, 64, 2, max_depth=6, rr_depth=3)
     rad, film, n_ext, n_sh = host.render(p)

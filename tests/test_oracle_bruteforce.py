@@ -128,9 +128,11 @@ def test_oracle_traversal_agrees_with_brute_force(scene_loader, name, n_rays):
 
 
 # ---- randomised scenes: shapes the four fixed scenes do not have --------------------------------------------------
-def _random_scene_json(rng, n_instances):
+def _random_scene_json(rng, n_instances, emitters="quad"):
     """Triangle soups and spheres under random scale / rotation / translation, some primitives shared by several
-    instances (TLAS + shared BLAS), a node hierarchy two levels deep (nested transforms, Scene.fs:38-49)."""
+    instances (TLAS + shared BLAS), a node hierarchy two levels deep (nested transforms, Scene.fs:38-49).
+    emitters="mixed": besides the two-sided quad, a one-sided sphere emitter and a one-sided quad of other colours
+    (drawn after everything else, so the geometry of a seed is the same in both modes)."""
     import json
     prims = []
     for _ in range(int(rng.integers(1, 5))):
@@ -152,8 +154,18 @@ def _random_scene_json(rng, n_instances):
     for i in range(n_instances + 1):
         nodes.append({"instances": [i], "transform": i % len(transforms)})
         nodes[1 + i % 3]["children"].append(len(nodes) - 1)
+    lights = [{"type": "diffuse", "emission": [1, 1, 1]}]
+    if emitters == "mixed":
+        lights += [{"type": "diffuse", "emission": [3.0, 0.5, 0.2], "two-sided": False}, {"type": "diffuse", "emission": [0.2, 0.6, 2.5], "two-sided": False}]
+        prims.append({"type": "sphere", "radius": float(rng.uniform(0.4, 1.2))})
+        for prim, light in ((len(prims) - 1, 1), (len(prims) - 2, 2)):
+            instances.append({"primitive": prim, "light": light})
+            transforms.append({"keyframes": [{"scale": [float(x) for x in rng.uniform(0.5, 2.0, 3)], "rotation": [float(x) for x in rng.uniform(-3, 3, 3)],
+                                              "translation": [float(x) for x in rng.uniform(-6, 6, 3)]}]})
+            nodes.append({"instances": [len(instances) - 1], "transform": len(transforms) - 1})
+            nodes[0]["children"].append(len(nodes) - 1)
     return json.dumps({"nodes": nodes, "instances": instances, "transforms": transforms, "primitives": prims,
-                       "materials": [{"type": "lambertian"}], "lights": [{"type": "diffuse", "emission": [1, 1, 1]}],
+                       "materials": [{"type": "lambertian"}], "lights": lights,
                        "integrator": {"type": "path-tracing", "spp": 1}, "camera": {"type": "pinhole"},
                        "film": {"width": 8, "height": 8, "tone-mapping": "identity"}})
 

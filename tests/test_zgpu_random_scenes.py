@@ -43,10 +43,10 @@ def test_hits_on_randomised_scenes(seed, n_instances):
     scene.close()
 
 
-@pytest.mark.parametrize("seed,n_instances", [(227, 6), (217, 40), (228, 40)])   # seeds whose camera sees lit geometry
-def test_films_on_randomised_scenes(seed, n_instances):
+@pytest.mark.parametrize("seed,n_instances,emitters", [(227, 6, "quad"), (217, 40, "quad"), (228, 40, "quad"), (227, 6, "mixed"), (217, 40, "mixed")])   # seeds whose camera sees lit geometry
+def test_films_on_randomised_scenes(seed, n_instances, emitters):
     oracle_ffi.set_portable_math(True)
-    scene = Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n_instances))
+    scene = Scene.LoadString(_random_scene_json(np.random.default_rng(seed), n_instances, emitters))
     oracle, gpu = OracleScene(scene.desc), scene.gpu()
     p = make_params(96, 64, 4, max_depth=6, rr_depth=3)
     film, st = gpu.render(p)
