@@ -120,6 +120,7 @@ _VP = C.c_void_p
 SYMBOLS = {
     "bn_device_count": (C.c_int, []),
     "bn_last_error": (C.c_char_p, []),
+    "bn_release_cached_buffers": (C.c_int, [C.c_int]),
     "bn_measure_l2_read_gbs": (C.c_int, [C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "bn_scene_create": (C.c_int, [C.POINTER(BnSceneDesc), C.c_int, C.POINTER(_VP)]),
     "bn_scene_destroy": (None, [_VP]),

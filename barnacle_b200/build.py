@@ -49,20 +49,21 @@ def _all_inputs() -> list[str]:
 
 def build(force: bool = False, verbose: bool = False, stats: bool = False, defines: list[str] | None = None, out: str | None = None) -> str:
     """stats=True: debug build with traversal phase counters (-DBN_TRAV_STATS); never shipped.
-    defines/out: experiment variants (tools/), written next to the real library."""
-    global LIB
+    defines/out: experiment variants (tools/).  A variant (stats, defines or out) NEVER touches the shipped library, its
+    objects or the CLI: it gets its own output name (default lib_stats.so / lib_variant.so, selected at run time with
+    BN_LIB=...) and its own object directory."""
     defines = defines or []
-    lib_real = LIB
-    if out:
-        LIB = os.path.join(LIB_DIR, out)
-    try:
-        return _build(force or bool(out) or bool(defines), verbose, stats, defines)
-    finally:
-        LIB = lib_real
+    variant = stats or bool(defines) or bool(out)
+    if not variant:
+        return _build(force, verbose, False, [], LIB, OBJ_DIR, True)
+    name = out or ("lib_stats.so" if stats and not defines else "lib_variant.so")
+    if os.path.abspath(os.path.join(LIB_DIR, name)) == os.path.abspath(LIB):
+        raise ValueError("a variant build must not be written over the shipped library")
+    return _build(True, verbose, stats, defines, os.path.join(LIB_DIR, name), os.path.join(OBJ_DIR, os.path.splitext(name)[0]), False)
 
 
-def _build(force: bool, verbose: bool, stats: bool, defines: list[str]) -> str:
-    if not force and not stats and _newer(LIB, _all_inputs()):
+def _build(force: bool, verbose: bool, stats: bool, defines: list[str], LIB: str, OBJ_DIR: str, with_cli: bool) -> str:
+    if not force and _newer(LIB, _all_inputs()):
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
     objs = []
@@ -78,6 +79,8 @@ def _build(force: bool, verbose: bool, stats: bool, defines: list[str]) -> str:
         objs.append(obj)
     cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static"]
     _run(cmd, verbose)
+    if not with_cli:
+        return LIB
     # C++ CLI mirroring Program.fs (links the C ABI only)
     cli = os.path.join(LIB_DIR, "barnacle_gpu")
     _run([HOST_CXX, "-std=c++17", "-O2", os.path.join(CSRC, "cli", "barnacle_gpu.cpp"), "-o", cli, "-L" + LIB_DIR, "-lbarnacle_b200",

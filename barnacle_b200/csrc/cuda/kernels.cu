@@ -47,6 +47,9 @@ constexpr int kBlock = 128;
 #ifndef BN_COUNTER_STRIDE
 #define BN_COUNTER_STRIDE 64   // ints between two queue counters / cursors (256 B)
 #endif
+#ifndef BN_INKERNEL_DRAIN
+#define BN_INKERNEL_DRAIN 1    // 0: every traversal launch is followed by a fix-up launch (A/B of the folded fix-up)
+#endif
 #ifndef BN_TRAV_GRID_MULT
 #define BN_TRAV_GRID_MULT 9    // persistent grid = SMs x this
 #endif
@@ -153,10 +156,41 @@ struct ExtendIO {
   BN_DEV void defer(int i) const { deferred.push(i); }
   BN_DEV void prefetch(int i) const { prefetch_l2(s0 + i); prefetch_l2(s1 + i); }
 };
+// The deferred rays (zero / denormal direction component: normally none, a handful at most) re-traced with the exact form.
+// Out of line on purpose: the hot loop's register allocation must not see this code.
 template <bool ANY, class IO>
-__global__ void __launch_bounds__(kBlock, BN_TRAV_MIN_BLOCKS) k_traverse(DScene sc, IO io) {
+BN_DEV void drain_deferred(const DScene& sc, const IO& io) {
+  const int n_deferred = *reinterpret_cast<volatile int*>(io.deferred.count);
+  for (int k = threadIdx.x; k < n_deferred; k += blockDim.x) {
+    const int i = reinterpret_cast<volatile int*>(io.deferred.list)[k];
+    float3 o, d;
+    float t;
+    io.load(i, o, d, t);
+    TraceResult r;
+    trace_exact<ANY>(sc, o, d, t, r);
+    io.store(i, r);
+  }
+}
+// `done` != nullptr: the CTA that finishes LAST (ticket counter) drains the deferred list itself, so no fix-up launch
+// follows (render path: 2 launches per bounce saved, whether or not a ray was deferred).  `done` == nullptr: the caller
+// launches k_traverse_fixup afterwards (bn_trace and BN_RENDER_FORCE_EXACT, where deferral is the rule, not the exception).
+template <bool ANY, class IO>
+__global__ void __launch_bounds__(kBlock, BN_TRAV_MIN_BLOCKS) k_traverse(const __grid_constant__ DScene sc, const __grid_constant__ IO io, int* done) {
   __shared__ uint32_t s_cold[kTravColdWords * kBlock];
   traverse_persistent<ANY>(sc, io, s_cold + threadIdx.x, kBlock);
+#if BN_INKERNEL_DRAIN
+  if (done != nullptr) {
+    __shared__ int s_last;
+    __threadfence();  // this thread's deferred-list appends and result stores, before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1) == (int)gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      drain_deferred<ANY>(sc, io);
+    }
+  }
+#endif
 }
 template <bool ANY, class IO>
 __global__ void __launch_bounds__(kBlock) k_traverse_fixup(DScene sc, IO io) {
@@ -448,6 +482,7 @@ void free_wave_buffers(WaveBuffers& w) {
 void release_wave_buffers(BnScene* s) {  // park the scene's buffers for the next scene on this device
   if (s->cap == 0 && !s->counters && !s->shadow_ref && !s->film && !s->arena) return;
   WaveBuffers w;
+  const bool park = std::getenv("BN_NO_BUFFER_CACHE") == nullptr;  // a host that shares the GPU can opt out of the retained footprint
   w.device = s->device; w.cap = s->cap;
   w.state[0] = s->state[0]; w.state[1] = s->state[1]; w.hits = s->hits; w.shq = s->shq; w.rad = s->rad; w.defer_list = s->defer_list;
   w.counters = s->counters; w.counters_len = s->counters_len; w.shadow_ref = s->shadow_ref; w.film = s->film; w.film_len = s->film_len;
@@ -456,6 +491,7 @@ void release_wave_buffers(BnScene* s) {  // park the scene's buffers for the nex
   s->cap = 0;
   s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
   s->counters = nullptr; s->counters_len = 0; s->shadow_ref = nullptr; s->film = nullptr; s->film_len = 0;
+  if (!park) { free_wave_buffers(w); return; }
   std::lock_guard<std::mutex> lock(g_pool_mutex);
   for (WaveBuffers& p : g_pool)
     if (p.device == w.device) {
@@ -482,19 +518,30 @@ void adopt_parked_buffers(BnScene* s) {
     }
 }
 
+constexpr int BN_ERR_NOMEM_RETRY = -100;  // internal: cudaErrorMemoryAllocation while growing the wave buffers (never leaves this file)
+
 int ensure_wave_buffers(BnScene* s, size_t cap) {
   if (s->cap >= cap) return BN_OK;
-
-  for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list})
-    if (p) cudaFree(p);
-  s->cap = 0;
-  s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
-  BN_CUDA(cudaMalloc((void**)&s->state[0], cap * 3 * sizeof(float4)));
-  BN_CUDA(cudaMalloc((void**)&s->state[1], cap * 3 * sizeof(float4)));
-  BN_CUDA(cudaMalloc((void**)&s->hits, cap * sizeof(float4)));
-  BN_CUDA(cudaMalloc((void**)&s->shq, cap * 4 * sizeof(float4)));
-  BN_CUDA(cudaMalloc((void**)&s->rad, cap * sizeof(float4)));
-  BN_CUDA(cudaMalloc((void**)&s->defer_list, cap * sizeof(int)));
+  auto drop = [&]() {
+    for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list})
+      if (p) cudaFree(p);
+    s->cap = 0;
+    s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
+  };
+  drop();
+  const struct { void** p; size_t bytes; } want[] = {
+      {(void**)&s->state[0], cap * 3 * sizeof(float4)}, {(void**)&s->state[1], cap * 3 * sizeof(float4)}, {(void**)&s->hits, cap * sizeof(float4)},
+      {(void**)&s->shq, cap * 4 * sizeof(float4)},      {(void**)&s->rad, cap * sizeof(float4)},          {(void**)&s->defer_list, cap * sizeof(int)}};
+  for (const auto& w : want) {
+    const cudaError_t e = cudaMalloc(w.p, w.bytes);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();  // not sticky
+      drop();
+      bnhost::set_error("out of device memory for the wave buffers");
+      return BN_ERR_NOMEM_RETRY;
+    }
+    if (!cuda_ok(e, "cudaMalloc(wave buffers)")) { drop(); return BN_ERR_CUDA; }
+  }
   s->cap = cap;
   return BN_OK;
 }
@@ -523,9 +570,9 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
   const int nbx = (rw + 7) / 8, nby = il_count > 1 ? owned_rows * 4 : (rh + 3) / 4;
   const long long total_blocks = (long long)nbx * nby;
   uint64_t launches = 0;
-  cudaEvent_t ev0, ev1;
-  BN_CUDA(cudaEventCreate(&ev0));
-  BN_CUDA(cudaEventCreate(&ev1));
+  if (!s->ev_begin) BN_CUDA(cudaEventCreate(&s->ev_begin));  // owned by the scene: nothing to leak on the error returns below
+  if (!s->ev_end) BN_CUDA(cudaEventCreate(&s->ev_end));
+  const cudaEvent_t ev0 = s->ev_begin, ev1 = s->ev_end;
   if (d_film) BN_CUDA(cudaMemsetAsync(d_film, 0, sizeof(float) * 3 * (size_t)p->width * p->height, stream));
   BN_CUDA(cudaEventRecord(ev0, stream));
   uint64_t n_paths = 0;
@@ -533,12 +580,19 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
   // bounces per path: PathTracing maxDepth | Direct: the hit and one BSDF-sampled ray | Normal: the hit
   const int D_bounces = p->integrator == BN_INTEGRATOR_DIRECT ? 2 : (p->integrator == BN_INTEGRATOR_NORMAL ? 1 : p->max_depth);
   if (total_blocks > 0 && ns > 0 && D_bounces > 0) {
-    const size_t cap_target = wave_capacity_paths();
-    long long blocks_per_wave = std::min<long long>(total_blocks, std::max<long long>(1, (long long)(cap_target / 32)));
-    int samples_per_wave = (int)std::max<long long>(1, std::min<long long>(ns, (long long)cap_target / (blocks_per_wave * 32)));
-    const size_t cap = (size_t)blocks_per_wave * 32 * samples_per_wave;
-    int rc = ensure_wave_buffers(s, cap);
-    if (rc != BN_OK) return rc;
+    size_t cap_target = wave_capacity_paths();
+    long long blocks_per_wave = 0;
+    int samples_per_wave = 0;
+    for (;;) {
+      blocks_per_wave = std::min<long long>(total_blocks, std::max<long long>(1, (long long)(cap_target / 32)));
+      samples_per_wave = (int)std::max<long long>(1, std::min<long long>(ns, (long long)cap_target / (blocks_per_wave * 32)));
+      const size_t cap = (size_t)blocks_per_wave * 32 * samples_per_wave;
+      const int rc = ensure_wave_buffers(s, cap);
+      if (rc == BN_OK) break;
+      // a smaller or shared GPU: 64 Mi paths want 13 GB of queues — halve the wave instead of failing the render
+      if (rc != BN_ERR_NOMEM_RETRY || cap_target <= ((size_t)1 << 18)) return rc == BN_ERR_NOMEM_RETRY ? BN_ERR_CUDA : rc;
+      cap_target /= 2;
+    }
     const long long n_block_chunks = (total_blocks + blocks_per_wave - 1) / blocks_per_wave;
     const long long n_sample_chunks = (ns + samples_per_wave - 1) / samples_per_wave;
     const long long n_waves = n_block_chunks * n_sample_chunks;
@@ -548,7 +602,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     // with one atomic per warp per 32 paths, and atomics that share a cache line are serialised by
     // the L2 slice that owns the line (BN_COUNTER_STRIDE ints apart = different lines / slices).
     constexpr size_t CS = BN_COUNTER_STRIDE;
-    const size_t per_wave = ((size_t)(D + 1) + D + 3 * (size_t)D + 2 * (size_t)D) * CS;
+    const size_t per_wave = ((size_t)(D + 1) + D + 3 * (size_t)D + 2 * (size_t)D + 2 * (size_t)D) * CS;  // ... + finished-CTA tickets 2 per bounce
     const size_t need = per_wave * (size_t)n_waves;
     if (s->counters_len < need) {
       if (s->counters) cudaFree(s->counters);
@@ -563,6 +617,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     const int tgrid = s->num_sms * BN_TRAV_GRID_MULT;
     DScene dsc = s->d;
     if (p->flags & BN_RENDER_FORCE_EXACT) dsc.all_finite = 0u;  // every ray is deferred to the exact fix-up kernel
+    const bool separate_fixup = !BN_INKERNEL_DRAIN || (p->flags & BN_RENDER_FORCE_EXACT) != 0 || std::getenv("BN_SEPARATE_FIXUP") != nullptr;
     // BN_RENDER_PROFILE: bracket every launch with events on the launching stream
     const bool profile = (p->flags & BN_RENDER_PROFILE) != 0 && stats != nullptr;
     std::vector<int> ev_class;  // 0 extend, 1 shade, 2 shadow, 3 other
@@ -603,6 +658,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         int* n_shadow = base + (size_t)(D + 1) * CS;
         int* cursors = base + (size_t)((D + 1) + D) * CS;
         int* n_defer = cursors + (size_t)(3 * D) * CS;
+        int* n_done = n_defer + (size_t)(2 * D) * CS;
         const size_t cp = s->cap;
         float4* A = s->state[0];
         float4* B = s->state[1];
@@ -613,8 +669,10 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         for (int b = 0; b < D; ++b) {
           prof_begin(0);
           const ExtendIO eio{A, A + cp, s->hits, n_active + b * CS, cursors + (3 * b) * CS, DeferList{n_defer + (2 * b) * CS, s->defer_list}};
-          k_traverse<false, ExtendIO><<<tgrid, kBlock, 0, stream>>>(dsc, eio);
-          k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
+          // the last CTA to finish drains the deferred rays; with BN_RENDER_FORCE_EXACT every ray is deferred and a
+          // full-width fix-up launch does the work instead
+          k_traverse<false, ExtendIO><<<tgrid, kBlock, 0, stream>>>(dsc, eio, separate_fixup ? nullptr : n_done + (2 * b) * CS);
+          if (separate_fixup) k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
           prof_end();
           prof_begin(1);
           k_shade<<<s->num_sms * BN_SHADE_MIN_BLOCKS, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
@@ -623,10 +681,10 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
           prof_end();
           prof_begin(2);
           const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b * CS, cursors + (3 * b + 2) * CS, DeferList{n_defer + (2 * b + 1) * CS, s->defer_list}};
-          k_traverse<true, ShadowIO><<<tgrid, kBlock, 0, stream>>>(dsc, sio);
-          k_traverse_fixup<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
+          k_traverse<true, ShadowIO><<<tgrid, kBlock, 0, stream>>>(dsc, sio, separate_fixup ? nullptr : n_done + (2 * b + 1) * CS);
+          if (separate_fixup) k_traverse_fixup<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
           prof_end();
-          launches += 5;
+          launches += separate_fixup ? 5 : 3;
           std::swap(A, B);
         }
         prof_begin(3);
@@ -636,7 +694,10 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         ++launches;
       }
     }
-    BN_CUDA(cudaGetLastError());
+    {
+      const cudaError_t le = cudaGetLastError();  // a failed launch leaves the queues half-built: the scene is unusable from here
+      if (le != cudaSuccess) { s->poisoned = true; cuda_ok(le, "kernel launch"); return BN_ERR_CUDA; }
+    }
     h_counters.resize(need);
     BN_CUDA(cudaEventRecord(ev1, stream));
     BN_CUDA(cudaMemcpyAsync(h_counters.data(), s->counters, need * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -679,8 +740,6 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     stats->gpu_ms = ms;
     stats->kernel_launches = launches;
   }
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   return BN_OK;
 }
 
@@ -723,6 +782,20 @@ int bn_measure_l2_read_gbs(int device, uint64_t bytes, int iters, double* gbs) {
   cudaFree(buf); cudaFree(sink);
   if (e != cudaSuccess || ms <= 0.f) { bnhost::set_error("L2 probe failed"); return BN_ERR_CUDA; }
   *gbs = (double)n_vec * 16.0 * iters / (ms * 1e-3) / 1e9;
+  return BN_OK;
+}
+
+int bn_release_cached_buffers(int device) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (size_t k = 0; k < g_pool.size();) {
+    if (device < 0 || g_pool[k].device == device) {
+      cudaSetDevice(g_pool[k].device);
+      free_wave_buffers(g_pool[k]);
+      g_pool.erase(g_pool.begin() + (long)k);
+    } else {
+      ++k;
+    }
+  }
   return BN_OK;
 }
 
@@ -772,6 +845,10 @@ void bn_scene_destroy(BnScene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+  if (s->ev_begin) cudaEventDestroy(s->ev_begin);
+  if (s->ev_end) cudaEventDestroy(s->ev_end);
+  if (s->trace_ctr) cudaFree(s->trace_ctr);
+  if (s->trace_dlist) cudaFree(s->trace_dlist);
   release_wave_buffers(s);  // parks the wave, counter and film buffers for the next scene on this device
   for (void* p : {(void*)s->mlt_f, (void*)s->mlt_i, (void*)s->mlt_w, (void*)s->mlt_cnt, (void*)s->mlt_acc})
     if (p) cudaFree(p);
@@ -838,14 +915,26 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
   const uint64_t chunk = 1ull << 28;
   const int n_chunks = (int)((n + chunk - 1) / chunk);
   // per chunk: cursor, deferred count; one deferred list shared by the (stream-ordered) chunks
-  int* ctr = nullptr;
-  int* dlist = nullptr;
-  BN_CUDA(cudaMalloc((void**)&ctr, sizeof(int) * 2 * (size_t)std::max(n_chunks, 1)));
-  BN_CUDA(cudaMalloc((void**)&dlist, sizeof(int) * (size_t)std::max<uint64_t>(std::min<uint64_t>(chunk, n), 1)));
-  BN_CUDA(cudaMemsetAsync(ctr, 0, sizeof(int) * 2 * (size_t)std::max(n_chunks, 1), stream));
-  cudaEvent_t e0, e1;
-  BN_CUDA(cudaEventCreate(&e0));
-  BN_CUDA(cudaEventCreate(&e1));
+  // scratch kept with the scene and grown on demand (no driver allocation in a warm call, nothing to leak on an error return)
+  const size_t want_ctr = 2 * (size_t)std::max(n_chunks, 1), want_dlist = (size_t)std::max<uint64_t>(std::min<uint64_t>(chunk, n), 1);
+  if (s->trace_ctr_len < want_ctr) {
+    if (s->trace_ctr) cudaFree(s->trace_ctr);
+    s->trace_ctr = nullptr; s->trace_ctr_len = 0;
+    BN_CUDA(cudaMalloc((void**)&s->trace_ctr, sizeof(int) * want_ctr));
+    s->trace_ctr_len = want_ctr;
+  }
+  if (s->trace_dlist_len < want_dlist) {
+    if (s->trace_dlist) cudaFree(s->trace_dlist);
+    s->trace_dlist = nullptr; s->trace_dlist_len = 0;
+    BN_CUDA(cudaMalloc((void**)&s->trace_dlist, sizeof(int) * want_dlist));
+    s->trace_dlist_len = want_dlist;
+  }
+  int* const ctr = s->trace_ctr;
+  int* const dlist = s->trace_dlist;
+  BN_CUDA(cudaMemsetAsync(ctr, 0, sizeof(int) * want_ctr, stream));
+  if (!s->ev_begin) BN_CUDA(cudaEventCreate(&s->ev_begin));
+  if (!s->ev_end) BN_CUDA(cudaEventCreate(&s->ev_end));
+  const cudaEvent_t e0 = s->ev_begin, e1 = s->ev_end;
   BN_CUDA(cudaEventRecord(e0, stream));
   const int grid = s->num_sms * 8;
   for (int c = 0; c < n_chunks; ++c) {
@@ -854,11 +943,11 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
     const int m = (int)std::min<uint64_t>(chunk, n - (uint64_t)c * chunk);
     if (any_hit) {
       const TraceIO<true> io{s->d, r, h, m, ctr + 2 * c, DeferList{ctr + 2 * c + 1, dlist}};
-      k_traverse<true, TraceIO<true>><<<grid, kBlock, 0, stream>>>(s->d, io);
+      k_traverse<true, TraceIO<true>><<<grid, kBlock, 0, stream>>>(s->d, io, nullptr);
       k_traverse_fixup<true, TraceIO<true>><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
     } else {
       const TraceIO<false> io{s->d, r, h, m, ctr + 2 * c, DeferList{ctr + 2 * c + 1, dlist}};
-      k_traverse<false, TraceIO<false>><<<grid, kBlock, 0, stream>>>(s->d, io);
+      k_traverse<false, TraceIO<false>><<<grid, kBlock, 0, stream>>>(s->d, io, nullptr);
       k_traverse_fixup<false, TraceIO<false>><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
     }
   }
@@ -867,10 +956,6 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
   if (e == cudaSuccess) e = cudaGetLastError();
   float t = 0.f;
   if (e == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(ctr);
-  cudaFree(dlist);
   if (e != cudaSuccess) { s->poisoned = true; cuda_ok(e, "bn_trace"); return BN_ERR_CUDA; }
   if (ms) *ms = t;
   return BN_OK;

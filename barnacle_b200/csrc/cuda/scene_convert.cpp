@@ -160,6 +160,11 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       err = "mesh slice out of range";
       return false;
     }
+    // AliasTable.Sample follows `alias` into the SAME mesh's table and triangle slice (light_sampler_sample, shade.cuh)
+    for (uint32_t t = 0; t < mm.tri_count; ++t) {
+      const int32_t a = d.alias[(size_t)mm.alias_offset + t].alias;
+      if (a < 0 || (uint32_t)a >= mm.tri_count) { err = "alias entry points outside its mesh's triangle slice"; return false; }
+    }
     TreeOut bt;
     if (!build_tree(d.blas_nodes + mm.node_offset, mm.node_count, mm.tri_count, (uint32_t)out.nodes.size(), mm.tri_offset, nullptr, out.nodes, bt, err, "BLAS")) return false;
     if (bt.depth > max_blas_depth) max_blas_depth = bt.depth;

@@ -37,6 +37,11 @@ struct BnScene {
   unsigned long long* mlt_cnt = nullptr;  // 4 counters
   unsigned int* mlt_acc = nullptr;
   size_t mlt_acc_len = 0;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // frame / batch timing (created once, destroyed with the scene)
+  int* trace_ctr = nullptr;      // bn_trace_device scratch: per-chunk cursor + deferred count
+  size_t trace_ctr_len = 0;
+  int* trace_dlist = nullptr;    // ... and its deferred list
+  size_t trace_dlist_len = 0;
   bool poisoned = false;
   std::vector<cudaEvent_t> events;  // BN_RENDER_PROFILE: start/stop pairs, one per kernel launch
 };

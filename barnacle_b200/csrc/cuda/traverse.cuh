@@ -262,7 +262,7 @@ template <> struct TravStack<true> {
   static BN_DEV bool pop(const uint32_t& e, float, uint32_t& cur) { cur = e; return true; }
 };
 template <bool ANY, class IO>
-BN_DEV void traverse_persistent(const DScene& sc, IO& io, uint32_t* __restrict__ cold, const int cold_stride) {
+BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __restrict__ cold, const int cold_stride) {
   typename TravStack<ANY>::type stk[kStackSize];
   // per-lane state
   float3 wo, winv;        // world-space ray (origin, 1/direction)

@@ -199,8 +199,9 @@ class GpuPathTracingIntegrator:
 class Scene:
     """Base/Scene.fs `Scene` + Loader.fs `Scene.Load` + Render.fs `Scene.Render`."""
 
-    def __init__(self, handle, lib):
+    def __init__(self, handle, lib, time_: float = 0.0, reload=None):
         self._h, self._lib = handle, lib
+        self._time, self._reload = float(time_), reload   # pose of the flattened scene; how to re-run Scene.Traverse at another t
         info = BnHostSceneInfo()
         lib.bn_host_scene_info(handle, C.byref(info))
         self.info = info
@@ -215,21 +216,27 @@ class Scene:
         """build_device: CUDA ordinal whose BVH builder (bn_bvh_build) builds every BLAS and the TLAS; None = host builder.
         The flattened scene is identical either way."""
         lib = _ffi.load()
-        h = C.c_void_p()
         bd = (base_dir or os.getcwd()).encode()
-        if build_device is None:
-            check(lib.bn_host_scene_load(filename.encode(), bd, C.c_float(time_), C.byref(h)), "Scene.Load")
-        else:
-            check(lib.bn_host_scene_load_ex(filename.encode(), bd, C.c_float(time_), int(build_device), C.byref(h)), "Scene.Load")
-        return Scene(h, lib)
+
+        def load_at(t: float):
+            h = C.c_void_p()
+            if build_device is None:
+                check(lib.bn_host_scene_load(filename.encode(), bd, C.c_float(t), C.byref(h)), "Scene.Load")
+            else:
+                check(lib.bn_host_scene_load_ex(filename.encode(), bd, C.c_float(t), int(build_device), C.byref(h)), "Scene.Load")
+            return h
+        return Scene(load_at(time_), lib, time_, load_at)
 
     @staticmethod
     def LoadString(text: str, base_dir: str | None = None, time_: float = 0.0) -> "Scene":
         lib = _ffi.load()
-        h = C.c_void_p()
         bd = (base_dir or os.getcwd()).encode()
-        check(lib.bn_host_scene_load_string(text.encode(), bd, C.c_float(time_), C.byref(h)), "Scene.Load")
-        return Scene(h, lib)
+
+        def load_at(t: float):
+            h = C.c_void_p()
+            check(lib.bn_host_scene_load_string(text.encode(), bd, C.c_float(t), C.byref(h)), "Scene.Load")
+            return h
+        return Scene(load_at(time_), lib, time_, load_at)
 
     @property
     def desc(self):
@@ -252,6 +259,7 @@ class Scene:
         """Render.fs:10-19.  Returns the seconds spent in Integrator.Render (the
         reference's Stopwatch region)."""
         self.Film.Clear()
+        self.Traverse(t)
         gpu = self.gpu(device)
         t0 = time.perf_counter()
         if self.integrator_type == "pssmlt":
@@ -270,6 +278,21 @@ class Scene:
         if filename:
             self.Film.Save(filename)
         return dt
+
+    def Traverse(self, t: float):
+        """Scene.Traverse(t) (Base/Scene.fs:38-61, called by every Render, Render.fs:10-13): instance transforms at time t,
+        then the TLAS and the light list over them.  The flattened scene holds ONE pose, so another t re-runs the host-side
+        builder (keyframe evaluation, instance bounds, BVHNode.Build) and drops the device copy of the old pose."""
+        if float(t) == self._time:
+            return
+        if self._reload is None:
+            raise BarnacleError(f"Scene.Render at t = {t}: this scene was flattened at t = {self._time} and cannot be re-traversed")
+        h = self._reload(float(t))
+        if self._gpu is not None:
+            self._gpu.close()
+            self._gpu = None
+        self._lib.bn_host_scene_destroy(self._h)
+        self._h, self._time = h, float(t)
 
     def close(self):
         if self._gpu is not None:

@@ -99,18 +99,28 @@ class ClockSampler:
                 "samples": len(rows), "reasons": reasons}
 
 
+def host_threads() -> int:
+    """The host threads this process may use.  Passed to the oracle EXPLICITLY: torchrun exports OMP_NUM_THREADS=1 to
+    every rank, and a CPU arm that follows it runs on one core (round 1's scaling record did exactly that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_sample(scene, w, h, spp_sample, counters: bool, libm: bool = True, keep_film: bool = False):
     """The CPU restatement on a bounded sample of the workload (all host threads)."""
     from barnacle_b200.scene import make_params
-    from oracle.oracle_ffi import OracleScene, num_threads, set_portable_math
+    from oracle.oracle_ffi import OracleScene, set_portable_math
     set_portable_math(not libm)
+    threads = host_threads()
     try:
         o = OracleScene(scene.desc)
         p = make_params(w, h, spp_sample, MAX_DEPTH, RR_DEPTH)
-        film, st = o.render(p, counters=counters)
+        film, st = o.render(p, counters=counters, threads=threads)
     finally:
         set_portable_math(True)
-    st["threads"] = num_threads()
+    st["threads"] = threads
     if keep_film:
         st["film"] = film
     return st
@@ -135,8 +145,11 @@ def run_reference(args, scene_file, W, H, SPP, label):
         return
     from barnacle_b200.scene import Scene
     scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
-    spp_s = max(1, args.ref_spp)
-    for _ in range(args.warmup):
+    # bounded sample per step, sized from one calibration pass so that the K timed steps take about a minute whatever the
+    # host (rates are spp-independent); --ref-spp pins it
+    t_cal = oracle_sample(scene, W, H, 1, False)["seconds"]
+    spp_s = args.ref_spp if args.ref_spp > 0 else max(1, min(SPP, int(args.ref_seconds / max(args.steps, 1) / max(t_cal, 1e-3))))
+    for _ in range(max(0, args.warmup - 1)):
         oracle_sample(scene, W, H, 1, False)
     rays = secs = paths = 0
     threads = 0
@@ -169,7 +182,7 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
     if args.impl == "reference":
         if rank != 0:
             return
-        from oracle.oracle_ffi import OracleScene, num_threads, set_portable_math
+        from oracle.oracle_ffi import OracleScene, set_portable_math
         scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
         i = scene.info
         set_portable_math(False)
@@ -178,7 +191,7 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
         rays = secs = muts = 0
         for k in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            _, st, _ = o.render_pssmlt(p)
+            _, st, _ = o.render_pssmlt(p, threads=host_threads())
             if k >= args.warmup:
                 secs += time.perf_counter() - t0; rays += st["rays"]; muts += st["proposed"]
         set_portable_math(True)
@@ -186,7 +199,7 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
         print(json.dumps({"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": label}, "mutations_per_s": muts / secs,
-                          "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": num_threads(), "kind": "port",
+                          "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": host_threads(), "kind": "port",
                                            "sample": "1 of 10 mutations per pixel, 262144 bootstrap paths, 1024 chains per step"},
                           "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -264,7 +277,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (the result is then NOT the named config)")
-    ap.add_argument("--ref-spp", type=int, default=4, help="--impl reference: spp of the bounded sample per step")
+    ap.add_argument("--ref-spp", type=int, default=0, help="--impl reference: spp of the bounded sample per step (0: sized so that the timed steps take about a minute)")
+    ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: CPU seconds the K timed steps should take together")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary `configs` lines (C1 / C3 / C4 at stated reduced spp)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     scene_file, W, H, SPP, label = WORKLOADS[args.workload]
@@ -280,7 +295,7 @@ def main():
     import torch
     import torch.distributed as dist
     from barnacle_b200 import _ffi
-    from barnacle_b200.multi_gpu import partition, render_sharded
+    from barnacle_b200.multi_gpu import partition, render_sharded, shard_params
     from barnacle_b200.scene import GpuScene, Scene, make_params
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -292,64 +307,110 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
-
-    scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
-    gpu = scene.gpu(local)
-    film = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    base = make_params(W, H, SPP, MAX_DEPTH, RR_DEPTH, flags=_ffi.BN_RENDER_PROFILE)
     stream = torch.cuda.current_stream().cuda_stream
+    lib = _ffi.load()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        flush.zero_()  # L2 flush between iterations
-        return render_sharded(gpu, base, film, dist if world > 1 else None, stream)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
-    t_wall0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot = {"extend": 0, "shadow": 0, "paths": 0, "launches": 0, "my_launches": 0, "extend_ms": 0.0, "shade_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0}
-    step_ms = []
-    barrier()
-    for _ in range(args.steps):
-        ev0.record()
-        st = step()
-        ev1.record()
-        torch.cuda.synchronize()
-        step_ms.append(ev0.elapsed_time(ev1))
-        if st is not None:
-            tot["extend"] += st.extend_rays; tot["shadow"] += st.shadow_rays; tot["paths"] += st.paths; tot["launches"] += st.kernel_launches
-            tot["extend_ms"] += st.extend_ms; tot["shade_ms"] += st.shade_ms; tot["shadow_ms"] += st.shadow_ms; tot["other_ms"] += st.other_ms
-            tot["render_ms"] += st.gpu_ms
-    barrier()
-    t_wall1 = time.time()
-    # flush.zero_() is inside ev0..ev1; subtract nothing — it is ~0.1 ms of a multi-hundred-ms step and is reported in config
-    my_ms = float(sum(step_ms))
-    agg = torch.tensor([my_ms, tot["extend"], tot["shadow"], tot["paths"], tot["launches"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = agg.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        total_ms = float(mx[0])
-    else:
+    def timed_steps(gpu, base, film, steps, warmup, mode):
+        """W untimed + K timed steps of one workload on this rank's shard; returns (max-over-ranks ms of the K steps,
+        job-wide totals, this rank's per-class ms, wall-clock bracket of the timed region)."""
+        def step():
+            flush.zero_()  # L2 flush between iterations
+            return render_sharded(gpu, base, film, dist if world > 1 else None, stream, mode)
+        for _ in range(warmup):
+            step()
+        barrier()
+        t_w0 = time.time()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = {"extend": 0, "shadow": 0, "paths": 0, "launches": 0, "extend_ms": 0.0, "shade_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0}
+        my_ms = 0.0
+        barrier()
+        for _ in range(steps):
+            ev0.record()
+            st = step()
+            ev1.record()
+            torch.cuda.synchronize()
+            my_ms += ev0.elapsed_time(ev1)   # flush.zero_() is inside: ~0.1 ms of a multi-hundred-ms step, stated in config
+            if st is not None:
+                tot["extend"] += st.extend_rays; tot["shadow"] += st.shadow_rays; tot["paths"] += st.paths; tot["launches"] += st.kernel_launches
+                tot["extend_ms"] += st.extend_ms; tot["shade_ms"] += st.shade_ms; tot["shadow_ms"] += st.shadow_ms; tot["other_ms"] += st.other_ms
+                tot["render_ms"] += st.gpu_ms
+        barrier()
+        t_w1 = time.time()
+        agg = torch.tensor([my_ms, tot["extend"], tot["shadow"], tot["paths"], tot["launches"], tot["extend_ms"], tot["shadow_ms"]], dtype=torch.float64, device="cuda")
         total_ms = my_ms
-    rays_total = float(agg[1] + agg[2])
-    paths_total = float(agg[3])
-    launches_total = int(agg[4])
+        if world > 1:
+            mx = agg.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            total_ms = float(mx[0])
+        job = {"extend": float(agg[1]), "shadow": float(agg[2]), "paths": float(agg[3]), "launches": int(agg[4]),
+               "extend_ms_sum": float(agg[5]), "shadow_ms_sum": float(agg[6])}   # *_ms_sum: device time of the class summed over ranks
+        return total_ms, job, tot, (t_w0, t_w1)
+
+    def l2_peak():
+        v = ctypes.c_double(0.0)
+        if lib.bn_measure_l2_read_gbs(local, 32 << 20, 20, ctypes.byref(v)) == 0 and v.value > 0:
+            return v.value
+        return None
+
+    def traversal_roofline(scene, w, h, job, l2_gbs):
+        """Extend (closest-hit traversal) against the L2 roofline: rays x algorithmic bytes per ray (instrumented oracle on a
+        bounded sample of this scene, REFERENCE layout and visiting order) / device time of the extend launches
+        (CUDA events on the launching stream, BN_RENDER_PROFILE; summed over ranks, so the rate is per GPU x ranks)."""
+        cw, ch = max(64, w // 8), max(64, h // 8)
+        cst = oracle_sample(scene, cw, ch, 2, True, libm=False)
+        b_ext = algorithmic_bytes_per_ray(cst["extend_counters"], B_IO_EXTEND)
+        b_sh = algorithmic_bytes_per_ray(cst["shadow_counters"], B_IO_SHADOW)
+        ext_s, sh_s = job["extend_ms_sum"] * 1e-3 / world, job["shadow_ms_sum"] * 1e-3 / world   # mean per-rank device time
+        per_gpu = (job["extend"] / world) * b_ext / ext_s / 1e9 if ext_s > 0 else None           # one GPU's rate vs one GPU's L2
+        return {"cw": cw, "ch": ch, "b_ext": b_ext, "b_sh": b_sh, "b_ext_cap": algorithmic_bytes_per_ray(cst["extend_counters"], B_IO_EXTEND, cap=True),
+                "achieved": per_gpu, "frac_l2": (per_gpu / l2_gbs) if per_gpu and l2_gbs else None,
+                "ext_rays_per_s": (job["extend"] / world) / ext_s if ext_s > 0 else None,
+                "sh_rays_per_s": (job["shadow"] / world) / sh_s if sh_s > 0 else None,
+                "sh_achieved": (job["shadow"] / world) * b_sh / sh_s / 1e9 if sh_s > 0 else None,
+                "counters": {k: cst["extend_counters"][k] / max(cst["extend_counters"]["rays"], 1) for k in cst["extend_counters"] if k != "rays"}}
+
+    scene = Scene.Load(os.path.join(ROOT, "scenes", scene_file), base_dir=ROOT)
+    gpu = scene.gpu(local)
+    film = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
+    base = make_params(W, H, SPP, MAX_DEPTH, RR_DEPTH, flags=_ffi.BN_RENDER_PROFILE)
+    # C4 is tile-split over the GPUs (BASELINE.json configs[3]); everything else by sampleId
+    mode = "tile" if (args.workload == "C4" and world > 1) else "auto"
+    clocks = ClockSampler(local) if rank == 0 else None
+    total_ms, job, tot, (t_wall0, t_wall1) = timed_steps(gpu, base, film, args.steps, args.warmup, mode)
+    rays_total = job["extend"] + job["shadow"]
+    paths_total = job["paths"]
+    launches_total = job["launches"]
     value = rays_total / (total_ms * 1e-3) / 1e6
+
+    # ---- N > 1: is the reduced film right?  Rank 0 renders the same seeds on its own GPU (outside every timed region) and
+    # compares with the film the last timed step left after the NCCL reduce.
+    multi_check = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            reduced = film.clone()
+            single = torch.zeros_like(film)
+            gpu.render_device(make_params(W, H, SPP, MAX_DEPTH, RR_DEPTH), single.data_ptr(), stream)
+            a, b = reduced.cpu().numpy(), single.cpu().numpy()
+            v, skipped = rel_mse(a, b)
+            multi_check = {"value": v, "eps": 1e-2, "non_finite_pixels_skipped": skipped, "max_abs_diff": float(np.nanmax(np.abs(a - b))),
+                           "bit_identical": bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all()),
+                           "vs": f"the same {W}x{H}x{SPP}spp frame rendered on ONE GPU (rank 0, outside the timed region) against the film left by the "
+                                 f"{world}-rank {'tile' if mode == 'tile' or SPP < world else 'sample'}-split step after the NCCL reduce; "
+                                 "sample split differs by fp32 reassociation of the per-pixel sum only, tile split not at all"}
+        barrier()
 
     # ---- e2e: through the C-ABI with host buffers (scene upload + film download per step)
     host_film = torch.empty(W * H * 3, dtype=torch.float32).pin_memory()
     host_film_np = host_film.numpy()
-    shard = partition(W, H, SPP, world, rank)
-    from barnacle_b200.multi_gpu import shard_params
+    shard = partition(W, H, SPP, world, rank, mode)
     sp = shard_params(make_params(W, H, SPP, MAX_DEPTH, RR_DEPTH), shard)
     d = scene.desc.contents
     h2d = (d.tlas_node_count + d.blas_node_count) * 32 + d.instance_count * 168 + d.vertex_count * 12 + d.triangle_count * 12 + d.alias_count * 12 + \
@@ -395,48 +456,76 @@ def main():
         e2e_s = float(mx[0])
     e2e_value = float(e2e_t[1]) / e2e_s / 1e6
 
+    l2_gbs = l2_peak() if rank == 0 else None
+
+    # ---- secondary configs: C1 / C3 / C4 at stated (reduced) spp so that the driver's record anchors every config, the
+    # weakest one (C4, tile-split at N > 1) included.  Same timing rules as the main line; 1 warm-up + 2 timed steps each.
+    SECONDARY_SPP = {"C1": 64, "C2": 32, "C3": 32, "C4": 8}
+    configs = {}
+    if not args.no_configs:
+        for name in ("C1", "C2", "C3", "C4"):
+            if name == args.workload:
+                continue
+            sf, w2, h2, spp_full, label2 = WORKLOADS[name]
+            spp2 = min(spp_full, SECONDARY_SPP[name])
+            mode2 = "tile" if (name == "C4" and world > 1) or spp2 < world else "sample"
+            sc2 = Scene.Load(os.path.join(ROOT, "scenes", sf), base_dir=ROOT)
+            g2 = sc2.gpu(local)
+            film2 = torch.zeros(w2 * h2 * 3, dtype=torch.float32, device="cuda")
+            ms2, job2, _, _ = timed_steps(g2, make_params(w2, h2, spp2, MAX_DEPTH, RR_DEPTH, flags=_ffi.BN_RENDER_PROFILE), film2, 2, 1, mode2)
+            if rank == 0:
+                rf = traversal_roofline(sc2, w2, h2, job2, l2_gbs)
+                configs[name] = {"workload": label2 + (f" [{spp2} of {spp_full} spp per step; rates are spp-independent]" if spp2 != spp_full else ""),
+                                 "value": (job2["extend"] + job2["shadow"]) / (ms2 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms2 / 2, "steps": 2, "warmup": 1,
+                                 "samples_per_s": job2["paths"] / (ms2 * 1e-3), "parallelism": "single GPU" if world == 1 else f"{mode2}-split x{world} + film reduce",
+                                 "extend_rays_per_s_per_gpu": rf["ext_rays_per_s"], "shadow_rays_per_s_per_gpu": rf["sh_rays_per_s"],
+                                 "roofline": {"bound": "l2", "achieved": rf["achieved"], "peak": l2_gbs, "unit": "GB/s", "frac": rf["frac_l2"],
+                                              "algorithmic_bytes_per_ray": rf["b_ext"]}}
+            g2.close()
+            sc2.close()
+            del film2
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+            hbm_peak, hbm_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
         else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        # algorithmic bytes per extend ray from the instrumented oracle on a bounded sample of this workload
-        cw, ch = max(64, W // 8), max(64, H // 8)
-        cst = oracle_sample(scene, cw, ch, 2, True, libm=False)
-        b_ext = algorithmic_bytes_per_ray(cst["extend_counters"], B_IO_EXTEND)
-        b_sh = algorithmic_bytes_per_ray(cst["shadow_counters"], B_IO_SHADOW)
-        ext_s = tot["extend_ms"] * 1e-3
-        achieved = tot["extend"] * b_ext / ext_s / 1e9 if ext_s > 0 else None
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        n_ext_launches = max(1, tot["launches"] // (2 + 5 * MAX_DEPTH) * MAX_DEPTH)   # launches per wave = 2 + 5*maxDepth, maxDepth of them are extends
-        if os.path.exists(tpath) and args.workload == "C2":
-            # ncu's DRAM bytes of ONE profiled extend launch, per ray of that launch, times the rays of this run's average
-            # launch: "per launch like achieved"
-            tj = json.load(open(tpath))
-            if tj.get("dram_bytes_per_ray"):
-                traffic = tj["dram_bytes_per_ray"] * tot["extend"] / n_ext_launches
-                traffic_src = tj["source"] + f"; {tj['dram_bytes_per_ray']:.1f} DRAM B/ray of the profiled launch x the rays of this run's average extend launch"
-            else:
-                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-        roofline = {"bound": "hbm", "kernel": "k_traverse<closest> (extend: TLAS+BLAS closest-hit traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": tot["extend"] * b_ext / n_ext_launches, "avg_launch_ms": tot["extend_ms"] / n_ext_launches,
-                    "algorithmic_bytes_per_ray": b_ext, "algorithmic_bytes_per_ray_cap152": algorithmic_bytes_per_ray(cst["extend_counters"], B_IO_EXTEND, cap=True),
-                    "rays_per_launch": tot["extend"] / n_ext_launches, "rays_per_s": tot["extend"] / ext_s if ext_s > 0 else None,
-                    "kernel_share_of_step": tot["extend_ms"] / tot["render_ms"] if tot["render_ms"] else None,
-                    "shadow": {"algorithmic_bytes_per_ray": b_sh, "achieved": (tot["shadow"] * b_sh / (tot["shadow_ms"] * 1e-3) / 1e9) if tot["shadow_ms"] else None,
-                               "rays_per_s": tot["shadow"] / (tot["shadow_ms"] * 1e-3) if tot["shadow_ms"] else None},
-                    "rank0_class_ms_per_step": {k: tot[k + "_ms"] / args.steps for k in ("extend", "shade", "shadow", "other")},
-                    "note": "bytes/ray = 32*N_node + 48*N_tri + (24*N_inst_visited + 64*N_inst_boxpass + 64*N_inst_committed) + 48 I/O in the REFERENCE layout (SURVEY 8d), counted by the instrumented oracle "
-                            f"on {cw}x{ch}x2spp of this scene; scene data is L2-resident, so this is an algorithmic-traffic rate against the HBM copy peak"}
-        # second denominator: the scene data is L2-resident, so also state the rate against
-        # the L2 read bandwidth measured here, now (32 MiB buffer, 16-B loads bypassing L1)
-        l2 = ctypes.c_double(0.0)
-        if _ffi.load().bn_measure_l2_read_gbs(local, 32 << 20, 20, ctypes.byref(l2)) == 0 and l2.value > 0 and achieved:
-            roofline["l2"] = {"peak": l2.value, "unit": "GB/s", "frac": achieved / l2.value,
-                              "peak_source": "bn_measure_l2_read_gbs: 20 sweeps of a 32 MiB L2-resident buffer, ld.global.cg.v4, CUDA events, this run"}
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        rf = traversal_roofline(scene, W, H, job, l2_gbs)
+        # rank 0's launches per wave: raygen + accumulate + (extend, shade, shadow) per bounce; 5 per bounce when every
+        # traversal launch is followed by a fix-up launch (BN_SEPARATE_FIXUP / a BN_INKERNEL_DRAIN=0 build)
+        per_wave = next((2 + k * MAX_DEPTH for k in ((5, 3) if os.environ.get("BN_SEPARATE_FIXUP") else (3, 5)) if tot["launches"] % (2 + k * MAX_DEPTH) == 0), 2 + 3 * MAX_DEPTH)
+        n_ext_launches = max(1, tot["launches"] // per_wave * MAX_DEPTH)
+        rays_per_launch = tot["extend"] / n_ext_launches
+        # ncu figures of the committed kernel on this workload (profiles/ncu_summary.json, made by tools/ncu_to_json.py from the
+        # committed capture): per-ray numbers of ONE profiled launch, scaled to this run's average launch
+        ncu = {}
+        npath = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(npath):
+            ncu = json.load(open(npath)).get(args.workload, {})
+        ne = ncu.get("extend", {})
+        traffic = ne["dram_bytes_per_ray"] * rays_per_launch if ne.get("dram_bytes_per_ray") else None
+        roofline = {
+            # the scene data of every config is L2-resident (ncu: DRAM traffic is the ray queue in and the hit record out, ~5 % of
+            # the algorithmic bytes), so the memory roofline of the traversal is the L2 read bandwidth, measured in this run
+            "bound": "l2", "kernel": "k_traverse<closest> (extend: TLAS+BLAS closest-hit traversal)",
+            "achieved": rf["achieved"], "peak": l2_gbs, "unit": "GB/s", "frac": rf["frac_l2"],
+            "peak_source": "bn_measure_l2_read_gbs: 20 sweeps of a 32 MiB L2-resident buffer, ld.global.cg.v4, CUDA events, this run, rank 0's GPU",
+            "traffic": traffic, "traffic_source": (ncu.get("source", "") + f"; {ne['dram_bytes_per_ray']:.1f} DRAM B/ray of the profiled launch x the rays of this run's average extend launch") if traffic else None,
+            "lanes_per_inst": ne.get("lanes_per_inst"), "warp_inst_per_ray": ne.get("warp_inst_per_ray"), "ncu_source": ncu.get("source"),
+            "algorithmic_bytes_per_launch": rays_per_launch * rf["b_ext"], "avg_launch_ms": tot["extend_ms"] / n_ext_launches,
+            "algorithmic_bytes_per_ray": rf["b_ext"], "algorithmic_bytes_per_ray_cap152": rf["b_ext_cap"], "per_ray_counters": rf["counters"],
+            "rays_per_launch": rays_per_launch, "rays_per_s": rf["ext_rays_per_s"],
+            "kernel_share_of_step": tot["extend_ms"] / tot["render_ms"] if tot["render_ms"] else None,
+            "hbm": {"peak": hbm_peak, "peak_source": hbm_src, "frac_algorithmic": (rf["achieved"] / hbm_peak) if rf["achieved"] else None,
+                    "frac_dram_traffic": (traffic / (tot["extend_ms"] / n_ext_launches * 1e-3) / 1e9 / hbm_peak) if traffic and tot["extend_ms"] else None,
+                    "note": "frac_algorithmic divides traffic served by L1/L2 by a DRAM-copy peak (can exceed 1, says nothing); frac_dram_traffic is ncu's DRAM bytes over the same peak"},
+            "shadow": {"algorithmic_bytes_per_ray": rf["b_sh"], "achieved": rf["sh_achieved"], "frac": (rf["sh_achieved"] / l2_gbs) if rf["sh_achieved"] and l2_gbs else None,
+                       "rays_per_s": rf["sh_rays_per_s"], "lanes_per_inst": ncu.get("shadow", {}).get("lanes_per_inst"),
+                       "warp_inst_per_ray": ncu.get("shadow", {}).get("warp_inst_per_ray")},
+            "rank0_class_ms_per_step": {k: tot[k + "_ms"] / args.steps for k in ("extend", "shade", "shadow", "other")},
+            "note": "bytes/ray = 32*N_node + 48*N_tri + (24*N_inst_visited + 64*N_inst_boxpass + 64*N_inst_committed) + 48 I/O in the REFERENCE layout (SURVEY 8d), counted by the "
+                    f"instrumented oracle on {rf['cw']}x{rf['ch']}x2spp of this scene; achieved = one GPU's extend rays x bytes/ray / its extend device time"}
         cpu = relmse = None
         if not args.no_cpu_baseline and world == 1:
             # ~10-30 s of CPU work on all host threads: about 30 M paths of the workload's film (libm math, as the reference)
@@ -456,18 +545,21 @@ def main():
                                 "against the restatement with this library's fixed fp32 transcendentals the film is bit-identical (tests/)"}
             except Exception as e:  # a metric must never take the bench line down with it
                 relmse = {"value": None, "error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            relmse = multi_check
         out = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": label, "max_depth": MAX_DEPTH, "rr_depth": RR_DEPTH, "parallelism": f"sample-split x{world} + film reduce" if world > 1 else "single GPU",
+            "config": {"workload": label, "max_depth": MAX_DEPTH, "rr_depth": RR_DEPTH,
+                       "parallelism": (f"{'tile' if shard.interleave_count > 1 else 'sample'}-split x{world} + film reduce") if world > 1 else "single GPU",
                        "l2_flush": "256 MiB memset between steps", "wave_paths": int(os.environ.get("BN_WAVE_PATHS", 64 << 20))},
             "samples_per_s": paths_total / (total_ms * 1e-3),
             "rays_per_step": rays_total / args.steps, "paths_per_step": paths_total / args.steps,
             "gpu_launches": launches_total,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
                     "rank0_step_ms": [round(x, 2) for x in e2e_step_ms]},
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "relmse": relmse,
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "relmse": relmse, "configs": configs,
         }
         print(json.dumps(out))
     if world > 1:

@@ -59,3 +59,26 @@ def test_reference_arm_other_ranks_exit_without_work(root):
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_uses_every_host_thread_under_torchrun(root):
+    """torchrun exports OMP_NUM_THREADS=1 to its ranks; the CPU arm must not follow it (round 1's scaling record ran the
+    reference on one core for N >= 2).  The thread count is handed to the oracle explicitly."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--ref-spp", "1"], cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == bench.host_threads() == len(os.sched_getaffinity(0))
+    if bench.host_threads() > 1:
+        assert d["cpu_baseline"]["cores"] > 1
+
+
+def test_reference_arm_sizes_its_sample_for_about_a_minute(root):
+    """--ref-spp 0 (the default): the bounded sample is sized from a calibration pass; the line says what it was."""
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "5", "--warmup", "1", "--ref-seconds", "4"],
+                       cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=400)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["steps"] == 5 and "of 64 spp per step" in d["cpu_baseline"]["sample"]
+    assert d["ms_per_step"] * 5 < 30e3
