@@ -33,6 +33,30 @@ struct __align__(16) GNode {
 };
 static_assert(sizeof(GNode) == 64, "GNode must be 64 B");
 
+// 4-wide node of the fast traversal path: a binary node P collapsed with its two children L, R.  Slots 0, 1 hold L's
+// children (or L itself in slot 0 when L is a leaf), slots 2, 3 R's (or R in slot 2); an empty slot has an inverted box
+// (lo = +FLT_MAX, hi = -FLT_MAX: the slab test fails for every ray) and ref kWideEmpty.  The reference's stack walk
+// reaches the four grandchildren in the order [near(P).near, near(P).far, far(P).near, far(P).far], i.e. group L before
+// group R iff dir[axis_P] > 0, slot 0 before slot 1 iff dir[axis_L] > 0, slot 2 before slot 3 iff dir[axis_R] > 0; an
+// axis of 3 means "in slot order" (leaf children, TLAS leaves holding several instances).  Skipping the boxes of L and R
+// cannot change a fast-path result: a grandchild's box lies inside its parent's, and the slab test is monotone in the
+// box for finite non-NaN operands, so "grandchild passes" implies "child passes" with the same t (scene_convert.cpp
+// checks the containment and falls back to the binary nodes otherwise).
+// Planes are stored per axis for the four slots (SoA), so that the near / far plane of an axis is ONE 16-B load whose
+// address depends on the sign of the ray direction — no min / max / select per box: the hi planes sit 64 B after the lo
+// planes, so "near" / "far" is bit 6 of the address (the array is 128-B aligned).
+struct __align__(128) GWide {
+  float lo[3][4];    //   +0: lo.x of slots 0..3 | +16: lo.y | +32: lo.z
+  uint32_t ref[4];   //  +48: child refs (same encoding as GNode.left / right; interior = ABSOLUTE GWide index)
+  float hi[3][4];    //  +64: hi.x               | +80: hi.y | +96: hi.z
+  uint32_t flips;    // +112: for each direction octant o = (dx>0) | (dy>0)<<1 | (dz>0)<<2, three bits at 3*o:
+                     //       bit 0 = slot 1 before slot 0, bit 1 = slot 3 before slot 2, bit 2 = group R before group L
+  uint32_t axes;     // +116: axis_P | axis_L << 2 | axis_R << 4 (what `flips` was derived from; 3 = "in slot order")
+  uint32_t pad[2];
+};
+static_assert(sizeof(GWide) == 128, "GWide must be 128 B");
+constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
+
 struct __align__(16) GTri {  // pre-gathered vertices of one BLAS-order triangle
   float p0[3]; float pad0;
   float p1[3]; float pad1;
@@ -58,7 +82,7 @@ struct __align__(16) GMesh {
 struct __align__(16) GInstTrav {
   float w2o[12];                      // rows 1..4 x columns 1..3 of WorldToObject
   float bmin[3]; uint32_t root;       // BLAS root bounds (MeshPrimitive.Bounds) + root ref | sphere: unused
-  float bmax[3]; uint32_t node_base;  // mesh's first GNode
+  float bmax[3]; uint32_t wroot;      // root ref in the 4-wide node array (fast path); == root when the BLAS is a single leaf
   uint32_t tri_base;                  // mesh's first GTri
   uint32_t is_sphere;
   float radius;
@@ -114,6 +138,9 @@ struct DScene {
   uint32_t n_inst, n_light_inst;
   uint32_t all_finite;       // every box / vertex / matrix is finite: the fast slab path is exact (vecmath.cuh)
   const GFlatInst* flat_tlas;  // [8][n_inst] or nullptr when n_inst > kFlatTlasMax
+  const GWide* wide;           // 4-wide nodes of the fast path (TLAS first, then every mesh), or nullptr: binary fast path
+  uint32_t tlas_wroot;         // TLAS root ref in `wide`
+  uint32_t pad_wide;
   GCamera cam;
 };
 

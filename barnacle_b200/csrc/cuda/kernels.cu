@@ -48,7 +48,10 @@ constexpr int kBlock = 128;
 #define BN_COUNTER_STRIDE 64   // ints between two queue counters / cursors (256 B)
 #endif
 #ifndef BN_INKERNEL_DRAIN
-#define BN_INKERNEL_DRAIN 1    // 0: every traversal launch is followed by a fix-up launch (A/B of the folded fix-up)
+#define BN_INKERNEL_DRAIN 0    // 1: the last CTA of a traversal launch drains the deferred rays itself (no fix-up launch). Measured on the B200
+                               // (profiles/r02_ab_session1.log): 26 instead of 42 launches per wave, but the drain's code costs the hot loop
+                               // three spilled registers — C1 -0.6 %, C2 -0.7 %, C3 -1.9 %, C4 -2.4 % — while the fix-up launches themselves
+                               // cost nothing measurable (same build with BN_SEPARATE_FIXUP: +0.1 %).  Off.
 #endif
 #ifndef BN_TRAV_GRID_MULT
 #define BN_TRAV_GRID_MULT 9    // persistent grid = SMs x this
@@ -174,10 +177,10 @@ BN_DEV void drain_deferred(const DScene& sc, const IO& io) {
 // `done` != nullptr: the CTA that finishes LAST (ticket counter) drains the deferred list itself, so no fix-up launch
 // follows (render path: 2 launches per bounce saved, whether or not a ray was deferred).  `done` == nullptr: the caller
 // launches k_traverse_fixup afterwards (bn_trace and BN_RENDER_FORCE_EXACT, where deferral is the rule, not the exception).
-template <bool ANY, class IO>
+template <bool ANY, bool WIDE, class IO>
 __global__ void __launch_bounds__(kBlock, BN_TRAV_MIN_BLOCKS) k_traverse(const __grid_constant__ DScene sc, const __grid_constant__ IO io, int* done) {
   __shared__ uint32_t s_cold[kTravColdWords * kBlock];
-  traverse_persistent<ANY>(sc, io, s_cold + threadIdx.x, kBlock);
+  traverse_persistent<ANY, WIDE>(sc, io, s_cold + threadIdx.x, kBlock);
 #if BN_INKERNEL_DRAIN
   if (done != nullptr) {
     __shared__ int s_last;
@@ -195,6 +198,13 @@ __global__ void __launch_bounds__(kBlock, BN_TRAV_MIN_BLOCKS) k_traverse(const _
 template <bool ANY, class IO>
 __global__ void __launch_bounds__(kBlock) k_traverse_fixup(DScene sc, IO io) {
   traverse_deferred<ANY>(sc, io, io.deferred.list, *io.deferred.count);
+}
+
+// host side: the 4-wide-node kernel when the scene has such nodes (sc.wide), else the binary-node kernel
+template <bool ANY, class IO>
+void launch_traverse(int grid, cudaStream_t stream, const DScene& sc, const IO& io, int* done) {
+  if (sc.wide != nullptr) k_traverse<ANY, true, IO><<<grid, kBlock, 0, stream>>>(sc, io, done);
+  else k_traverse<ANY, false, IO><<<grid, kBlock, 0, stream>>>(sc, io, done);
 }
 
 // ---- shade: one iteration of Li's loop body (PathTracing.fs:30-79) --------------------
@@ -671,7 +681,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
           const ExtendIO eio{A, A + cp, s->hits, n_active + b * CS, cursors + (3 * b) * CS, DeferList{n_defer + (2 * b) * CS, s->defer_list}};
           // the last CTA to finish drains the deferred rays; with BN_RENDER_FORCE_EXACT every ray is deferred and a
           // full-width fix-up launch does the work instead
-          k_traverse<false, ExtendIO><<<tgrid, kBlock, 0, stream>>>(dsc, eio, separate_fixup ? nullptr : n_done + (2 * b) * CS);
+          launch_traverse<false>(tgrid, stream, dsc, eio, separate_fixup ? nullptr : n_done + (2 * b) * CS);
           if (separate_fixup) k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
           prof_end();
           prof_begin(1);
@@ -681,7 +691,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
           prof_end();
           prof_begin(2);
           const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b * CS, cursors + (3 * b + 2) * CS, DeferList{n_defer + (2 * b + 1) * CS, s->defer_list}};
-          k_traverse<true, ShadowIO><<<tgrid, kBlock, 0, stream>>>(dsc, sio, separate_fixup ? nullptr : n_done + (2 * b + 1) * CS);
+          launch_traverse<true>(tgrid, stream, dsc, sio, separate_fixup ? nullptr : n_done + (2 * b + 1) * CS);
           if (separate_fixup) k_traverse_fixup<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
           prof_end();
           launches += separate_fixup ? 5 : 3;
@@ -814,6 +824,7 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   bnconv::ConvertedScene cs;
   std::string err;
   if (!bnconv::convert_scene(*desc, cs, err)) { bnhost::set_error(err); return BN_ERR_INVALID; }
+  if (std::getenv("BN_BINARY_NODES")) bnconv::use_binary_nodes(cs);  // A/B switch: the binary-node fast path
   BN_CUDA(cudaSetDevice(device));
   int cc_major = 0, sm_count = 0;  // (cudaGetDeviceProperties costs milliseconds per call; two attributes do not)
   BN_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
@@ -831,6 +842,10 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   arena.add(cs.sphere_radii, &d.sphere_radii); arena.add(cs.materials, &d.materials); arena.add(cs.lights, &d.lights); arena.add(cs.light_inst, &d.light_inst);
   d.flat_tlas = nullptr;
   if (!cs.flat_tlas.empty() && !std::getenv("BN_NO_FLAT_TLAS")) arena.add(cs.flat_tlas, &d.flat_tlas);
+  d.wide = nullptr;
+  if (!cs.wide.empty()) arena.add(cs.wide, &d.wide);
+  d.tlas_wroot = cs.tlas_wroot;
+  d.pad_wide = 0;
   if ((rc = arena.commit(s))) { bn_scene_destroy(s); return rc; }
   d.tlas = cs.tlas;
   d.n_inst = (uint32_t)cs.inst_head.size();
@@ -943,11 +958,11 @@ int bn_trace_device(BnScene* s, const void* d_rays, uint64_t n, int any_hit, voi
     const int m = (int)std::min<uint64_t>(chunk, n - (uint64_t)c * chunk);
     if (any_hit) {
       const TraceIO<true> io{s->d, r, h, m, ctr + 2 * c, DeferList{ctr + 2 * c + 1, dlist}};
-      k_traverse<true, TraceIO<true>><<<grid, kBlock, 0, stream>>>(s->d, io, nullptr);
+      launch_traverse<true>(grid, stream, s->d, io, nullptr);
       k_traverse_fixup<true, TraceIO<true>><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
     } else {
       const TraceIO<false> io{s->d, r, h, m, ctr + 2 * c, DeferList{ctr + 2 * c + 1, dlist}};
-      k_traverse<false, TraceIO<false>><<<grid, kBlock, 0, stream>>>(s->d, io, nullptr);
+      launch_traverse<false>(grid, stream, s->d, io, nullptr);
       k_traverse_fixup<false, TraceIO<false>><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
     }
   }

@@ -130,6 +130,102 @@ bool build_tree(const BnBVHNode* n, uint32_t count, uint32_t item_count, uint32_
   return true;
 }
 
+// ---- 4-wide nodes of the fast path (device_scene.h: GWide) -----------------------------------------------------------
+// Built from the binary GNode array above, so TLAS (with its pseudo chains) and BLAS go through the same code.
+struct WideBuilder {
+  const std::vector<bn::GNode>& nodes;
+  std::vector<bn::GWide>& wide;
+  bool ok = true;   // false: some box is not finite / not ordered / not inside its parent's — the binary path is used
+  int depth = 0;    // 4-wide levels of the tree being collapsed
+
+  static constexpr float kBig = 3.402823466e38f;
+  static bool is_link(const float* lo, const float* hi) { return lo[0] == -kBig && hi[0] == kBig; }  // chain link of a pseudo node
+  bool box_ok(const float* lo, const float* hi) {
+    if (is_link(lo, hi)) return true;
+    for (int a = 0; a < 3; ++a)
+      if (!std::isfinite(lo[a]) || !std::isfinite(hi[a]) || !(lo[a] <= hi[a])) return false;
+    return true;
+  }
+  static bool inside(const float* olo, const float* ohi, const float* ilo, const float* ihi) {
+    for (int a = 0; a < 3; ++a)
+      if (!(olo[a] <= ilo[a] && ihi[a] <= ohi[a])) return false;
+    return true;
+  }
+  void set_slot(bn::GWide& w, int k, const float* lo, const float* hi, uint32_t ref) {
+    if (!box_ok(lo, hi)) ok = false;
+    for (int a = 0; a < 3; ++a) { w.lo[a][k] = lo[a]; w.hi[a][k] = hi[a]; }
+    w.ref[k] = ref;
+  }
+  // instances of the pseudo chain that starts at interior node c (axis 3): 2 .. k
+  int chain_length(uint32_t c) const {
+    int n = 1;
+    while (!(c & bn::kLeafBit) && nodes[c].axis == 3u) { ++n; c = nodes[c].right; }
+    return n;
+  }
+  uint32_t child(uint32_t ref, int level) { return (ref & bn::kLeafBit) ? ref : collapse(ref, level); }
+
+  // `ref`: an interior GNode ref.  Returns the index of the GWide that stands for it.
+  uint32_t collapse(uint32_t ref, int level) {
+    const uint32_t idx = (uint32_t)wide.size();
+    wide.emplace_back();
+    if (level + 1 > depth) depth = level + 1;
+    bn::GWide w;
+    for (int a = 0; a < 3; ++a)
+      for (int k = 0; k < 4; ++k) { w.lo[a][k] = kBig; w.hi[a][k] = -kBig; }
+    for (int k = 0; k < 4; ++k) w.ref[k] = bn::kWideEmpty;
+    w.pad[0] = w.pad[1] = 0;
+    const bn::GNode P = nodes[ref];
+    if (P.axis == 3u) {
+      // TLAS leaf holding several instances (a chain of pseudo nodes): up to four of them in ONE wide node, in slot
+      // order (every axis 3); a longer leaf continues in slot 3 behind the chain's always-passing link box
+      uint32_t c = ref;
+      int k = 0;
+      for (;;) {
+        const bn::GNode C = nodes[c];
+        if (C.axis != 3u || !(C.left & bn::kLeafBit)) { ok = false; break; }
+        set_slot(w, k++, C.lmin, C.lmax, C.left);
+        if (C.right & bn::kLeafBit) { set_slot(w, k++, C.rmin, C.rmax, C.right); break; }
+        if (k == 3) { set_slot(w, 3, C.rmin, C.rmax, collapse(C.right, level + 1)); break; }
+        c = C.right;
+      }
+      w.axes = 3u | (3u << 2) | (3u << 4);
+    } else {
+      uint32_t axes = P.axis;
+      for (int g = 0; g < 2; ++g) {
+        const uint32_t c = g == 0 ? P.left : P.right;
+        const float* clo = g == 0 ? P.lmin : P.rmin;
+        const float* chi = g == 0 ? P.lmax : P.rmax;
+        uint32_t axis = 3u;
+        if ((c & bn::kLeafBit) || (nodes[c].axis == 3u && chain_length(c) > 2)) {
+          // a leaf, or a TLAS leaf of 3+ instances kept behind its own box (one more node visit only when that box passes)
+          for (uint32_t q = c; !(q & bn::kLeafBit); q = nodes[q].right) {  // ... which must hold every instance of the chain
+            if (!inside(clo, chi, nodes[q].lmin, nodes[q].lmax)) ok = false;
+            if ((nodes[q].right & bn::kLeafBit) && !inside(clo, chi, nodes[q].rmin, nodes[q].rmax)) ok = false;
+          }
+          set_slot(w, 2 * g, clo, chi, child(c, level + 1));
+        } else {
+          const bn::GNode C = nodes[c];
+          if (!inside(clo, chi, C.lmin, C.lmax) || !inside(clo, chi, C.rmin, C.rmax)) ok = false;
+          set_slot(w, 2 * g, C.lmin, C.lmax, child(C.left, level + 1));
+          set_slot(w, 2 * g + 1, C.rmin, C.rmax, child(C.right, level + 1));
+          axis = C.axis;
+        }
+        axes |= axis << (2 + 2 * g);
+      }
+      w.axes = axes;
+    }
+    // visiting order per direction octant: "left first iff dir[axis] > 0" (BVH.fs:51-56, Mesh.fs:235-240); axis 3 = slot order
+    w.flips = 0;
+    for (uint32_t oct = 0; oct < 8; ++oct) {
+      const uint32_t sg = oct | 8u;
+      const uint32_t fl = (((sg >> ((w.axes >> 2) & 3u)) & 1u) ? 0u : 1u) | (((sg >> ((w.axes >> 4) & 3u)) & 1u) ? 0u : 2u) | (((sg >> (w.axes & 3u)) & 1u) ? 0u : 4u);
+      w.flips |= fl << (3u * oct);
+    }
+    wide[idx] = w;
+    return idx;
+  }
+};
+
 void mat43(const float* m, bn::GMat43& o) {
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 3; ++c) o.m[r * 3 + c] = m[r * 4 + c];
@@ -226,7 +322,7 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       h.kind_prim = in.prim_id;
       const bn::GMesh& gm = out.meshes[in.prim_id];
       std::memcpy(tv.bmin, gm.tree.bmin, 12); std::memcpy(tv.bmax, gm.tree.bmax, 12);
-      tv.root = gm.tree.root; tv.node_base = gm.tree.node_base; tv.tri_base = gm.tri_base;
+      tv.root = gm.tree.root; tv.wroot = gm.tree.root; tv.tri_base = gm.tri_base;
       // Identity instances (e.g. the Cornell-box walls): Vector3.Transform by I returns its argument
       // bit for bit for the rays the fast path takes (no zero direction component; the sign of a
       // zero in the origin cannot reach a result), and the BLAS root box IS the instance's world
@@ -252,6 +348,36 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       err = "unknown primitive kind";
       return false;
     }
+  }
+  // 4-wide nodes of the fast path: the TLAS first, then every mesh.  Any box that is not finite / ordered / contained
+  // in its parent's switches the whole scene back to the binary nodes (a foreign host may hand over any tree).
+  {
+    WideBuilder wb{out.nodes, out.wide};
+    auto collapse_root = [&](uint32_t root, int& depth) {
+      wb.depth = 0;
+      const uint32_t r = (root & bn::kLeafBit) ? root : wb.collapse(root, 0);
+      depth = wb.depth;
+      return r;
+    };
+    int dt = 0, db_max = 0;
+    out.tlas_wroot = collapse_root(out.tlas.root, dt);
+    std::vector<uint32_t> mesh_wroot(d.mesh_count);
+    for (uint32_t m = 0; m < d.mesh_count; ++m) {
+      int db = 0;
+      mesh_wroot[m] = collapse_root(out.meshes[m].tree.root, db);
+      if (db > db_max) db_max = db;
+    }
+    out.max_stack_wide = 3 * (dt + db_max) + 2;   // every wide node on the current path leaves at most 3 entries
+    out.inst_wroot.assign(d.instance_count, bn::kWideEmpty);
+    for (uint32_t i = 0; i < d.instance_count; ++i)
+      if (d.instances[i].prim_kind == BN_PRIM_MESH) out.inst_wroot[i] = mesh_wroot[d.instances[i].prim_id];
+    if (!wb.ok || !out.all_finite || out.max_stack_wide > bn::kStackSize || out.wide.size() >= (1u << 30)) {
+      out.wide.clear();
+      out.inst_wroot.clear();
+      out.max_stack_wide = 0;
+    }
+    for (uint32_t i = 0; i < d.instance_count; ++i)
+      out.inst_trav[i].wroot = out.wide.empty() ? out.inst_trav[i].root : out.inst_wroot[i];
   }
   // Small-TLAS ordered scan (traverse.cuh): instance order of the reference's walk for each octant.
   // The walk visits left first iff dir[splitAxis] > 0 (Aggregate/BVH.fs:51-56) and leaf items in
@@ -281,7 +407,7 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
         const BnInstance& in = d.instances[order[k]];
         std::memcpy(f.bmin, in.bounds_min, 12); std::memcpy(f.bmax, in.bounds_max, 12);
         f.slot = order[k];
-        f.direct_root = out.inst_trav[order[k]].identity ? out.inst_trav[order[k]].root : 0xFFFFFFFFu;
+        f.direct_root = out.inst_trav[order[k]].identity ? out.inst_trav[order[k]].wroot : 0xFFFFFFFFu;  // (use_binary_nodes() re-points it)
       }
     }
   }
@@ -315,6 +441,16 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
   mat43(c.camera_to_world, cm);
   std::memcpy(out.cam.c2w, cm.m, sizeof cm.m);
   return true;
+}
+
+// A/B switch (BN_BINARY_NODES): drop the 4-wide nodes and point everything that names a BLAS root back at the binary tree.
+void use_binary_nodes(ConvertedScene& cs) {
+  cs.wide.clear();
+  cs.inst_wroot.clear();
+  cs.max_stack_wide = 0;
+  for (bn::GInstTrav& t : cs.inst_trav) t.wroot = t.root;
+  for (bn::GFlatInst& f : cs.flat_tlas)
+    if (f.direct_root != 0xFFFFFFFFu) f.direct_root = cs.inst_trav[f.slot].root;
 }
 
 }  // namespace bnconv

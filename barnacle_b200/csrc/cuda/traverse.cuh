@@ -60,6 +60,12 @@ constexpr int kRefillMinAny = BN_REFILL_MIN_ANY;  // ... for any-hit (shadow) ra
 #ifndef BN_STAY_T
 #define BN_STAY_T 4
 #endif
+#ifdef BN_EXP_ANY_UNORDERED   // (round-1 name of the switch)
+#define BN_ANY_UNORDERED 1
+#endif
+#ifndef BN_ANY_UNORDERED
+#define BN_ANY_UNORDERED 1
+#endif
 #ifndef BN_PREFETCH_AHEAD
 #define BN_PREFETCH_AHEAD 16384
 #endif
@@ -261,7 +267,10 @@ template <> struct TravStack<true> {
   static BN_DEV void push(uint32_t& e, uint32_t ref, float) { e = ref; }
   static BN_DEV bool pop(const uint32_t& e, float, uint32_t& cur) { cur = e; return true; }
 };
-template <bool ANY, class IO>
+// WIDE = true: interior refs index the 4-wide nodes (sc.wide, device_scene.h: GWide) and phase N is one step of such a
+// node — four slab tests, the passing children taken in the reference's visiting order; WIDE = false: the binary
+// two-box nodes (sc.nodes).  Leaves, phases T / E / S, the stack discipline and the results are the same.
+template <bool ANY, bool WIDE, class IO>
 BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __restrict__ cold, const int cold_stride) {
   typename TravStack<ANY>::type stk[kStackSize];
   // per-lane state
@@ -379,7 +388,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         } else {
           // BVHAggregate pops node 0 and tests its bounds first (BVH.fs:45-47)
           const Slab s = slab<true>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv);
-          if (slab_pass<true>(s, t)) cur = sc.tlas.root | kTlasBit;
+          if (slab_pass<true>(s, t)) cur = (WIDE ? sc.tlas_wroot : sc.tlas.root) | kTlasBit;
           else finish();
         }
       }
@@ -395,7 +404,52 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
       // costs five instructions per step to keep in a register.
       for (;;) {
         BN_STAT(0, __popc(__ballot_sync(kFull, (int)cur >= 0)));
-        if ((int)cur >= 0) {
+        if (WIDE) {
+          if ((int)cur >= 0) {
+            BN_WORK(135);
+            // ---- one 4-wide node (128 B): near / far planes of the four slots picked by the direction signs at the
+            // address level, so each box is 6 FADD + 6 FMUL and the two min / max chains of slab<true>
+            const uintptr_t nb = reinterpret_cast<uintptr_t>(sc.wide) + (size_t)(cur & kIndexMask) * 128u;
+            // near plane of an axis = lo if dir > 0, else hi (64 B further: bit 6 of the address); far = the other one
+            const uintptr_t ax = nb | ((signs & 1u) ? 0u : 64u), ay = nb | ((signs & 2u) ? 0u : 64u), az = nb | ((signs & 4u) ? 0u : 64u);
+            const float4 nx = __ldg(reinterpret_cast<const float4*>(ax)), fx = __ldg(reinterpret_cast<const float4*>(ax ^ 64u));
+            const float4 ny = __ldg(reinterpret_cast<const float4*>(ay) + 1), fy = __ldg(reinterpret_cast<const float4*>(ay ^ 64u) + 1);
+            const float4 nz = __ldg(reinterpret_cast<const float4*>(az) + 2), fz = __ldg(reinterpret_cast<const float4*>(az ^ 64u) + 2);
+            const uint4 rf = __ldg(reinterpret_cast<const uint4*>(nb) + 3);
+            // slab<true> + slab_pass<true> per slot; key = entry distance if the slot passes, else -1 (an entry distance is >= 1e-3)
+#define BN_WIDE_SLOT(c)                                                                                                         \
+            fmaxf(fmaxf(1e-3f, (nx.c - o.x) * inv.x), fmaxf((ny.c - o.y) * inv.y, (nz.c - o.z) * inv.z)) <=                      \
+                    fminf(t, fminf((fx.c - o.x) * inv.x, fminf((fy.c - o.y) * inv.y, (fz.c - o.z) * inv.z)))                     \
+                ? fmaxf(fmaxf(1e-3f, (nx.c - o.x) * inv.x), fmaxf((ny.c - o.y) * inv.y, (nz.c - o.z) * inv.z))                   \
+                : -1.f
+            float k0 = BN_WIDE_SLOT(x), k1 = BN_WIDE_SLOT(y), k2 = BN_WIDE_SLOT(z), k3 = BN_WIDE_SLOT(w);
+#undef BN_WIDE_SLOT
+            uint32_t r0 = rf.x, r1 = rf.y, r2 = rf.z, r3 = rf.w;
+            // the reference's order: group L (slots 0, 1) before group R (2, 3) iff dir[axis_P] > 0, slot 0 before 1 iff
+            // dir[axis_L] > 0, slot 2 before 3 iff dir[axis_R] > 0 (BVH.fs:51-56 / Mesh.fs:235-240 applied twice) — tabulated
+            // per direction octant in the node.  An any-hit query returns the same boolean whatever the order.
+            if (!ANY || !BN_ANY_UNORDERED) {
+              const uint32_t fl = __ldg(reinterpret_cast<const uint32_t*>(nb) + 28) >> ((signs & 7u) * 3u);
+              if (fl & 1u) { const uint32_t r = r0; r0 = r1; r1 = r; const float k = k0; k0 = k1; k1 = k; }
+              if (fl & 2u) { const uint32_t r = r2; r2 = r3; r3 = r; const float k = k2; k2 = k3; k3 = k; }
+              if (fl & 4u) {
+                uint32_t r = r0; r0 = r2; r2 = r; r = r1; r1 = r3; r3 = r;
+                float k = k0; k0 = k2; k2 = k; k = k1; k1 = k3; k3 = k;
+              }
+            }
+            const uint32_t level = cur & kTlasBit;
+            const bool q0 = k0 > 0.f, q1 = k1 > 0.f, q2 = k2 > 0.f, q3 = k3 > 0.f;
+            if (!(q0 || q1 || q2 || q3)) {
+              pop();
+            } else {
+              // the first passing child in visiting order is next; the others wait on the stack, nearest on top
+              if (q3 && (q0 || q1 || q2)) { TravStack<ANY>::push(stk[sp], r3 | level, k3); ++sp; }
+              if (q2 && (q0 || q1)) { TravStack<ANY>::push(stk[sp], r2 | level, k2); ++sp; }
+              if (q1 && q0) { TravStack<ANY>::push(stk[sp], r1 | level, k1); ++sp; }
+              cur = (q0 ? r0 : (q1 ? r1 : (q2 ? r2 : r3))) | level;
+            }
+          }
+        } else if ((int)cur >= 0) {
           BN_WORK(75);
           const float4* np = node_base + (size_t)(cur & kIndexMask) * 4u;
           const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
@@ -403,14 +457,10 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
           const Slab sr = slab<true>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv);
           const bool pl = slab_pass<true>(sl, t), pr = slab_pass<true>(sr, t);
           const uint32_t level = cur & kTlasBit;
-#ifdef BN_EXP_ANY_UNORDERED
-          // experiment queued for the next GPU session (default off): an any-hit query returns the same boolean whatever
-          // the visiting order (every box that passes is visited unless a hit ends the walk first), so shadow rays could
-          // skip the front-to-back bookkeeping: unoccluded rays save instructions, occluded ones may walk further
-          const bool lf = ANY ? true : ((signs >> fbits(n3.z)) & 1u) != 0u;
-#else
-          const bool lf = ((signs >> fbits(n3.z)) & 1u) != 0u;  // left first iff dir[splitAxis] > 0 (BVH.fs:51-56 / Mesh.fs:235-240)
-#endif
+          // left first iff dir[splitAxis] > 0 (BVH.fs:51-56 / Mesh.fs:235-240).  An any-hit query returns the same boolean
+          // whatever the visiting order (every box that passes is visited unless a hit ends the walk first), so shadow rays
+          // skip the front-to-back bookkeeping (BN_ANY_UNORDERED; measured on the B200: shadow rays +2..3 %)
+          const bool lf = (ANY && BN_ANY_UNORDERED) ? true : ((signs >> fbits(n3.z)) & 1u) != 0u;
           const uint32_t left = fbits(n3.x) | level, right = fbits(n3.y) | level;
           if (!pl) {  // branches on the two predicates as they are (no pl | pr to materialise)
             if (pr) cur = right;
@@ -471,18 +521,18 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         BN_WORK(70);
         const uint32_t slot = cur & kIndexMask;
         const float4* ip = reinterpret_cast<const float4*>(sc.inst_trav + slot);
-        const float4 m0 = __ldg(ip + 3), m2 = __ldg(ip + 5);
+        const float4 m0 = __ldg(ip + 3), m1 = __ldg(ip + 4), m2 = __ldg(ip + 5);
+        const uint32_t blas_root = WIDE ? fbits(m1.w) : fbits(m0.w);  // GInstTrav.wroot | root
         tri_k = 0;
         if (fbits(m2.w)) {
           // identity mesh instance: object space == world space, root box == instance box (passed)
           o = wo; d = f3(wdx, wdy, wdz); inv = winv; signs = wsigns;
           in_obj = true;
           cur_inst = (int)slot;
-          cur = fbits(m0.w);
+          cur = blas_root;
           continue;
         }
         const Mat43 M = load_mat43(ip);
-        const float4 m1 = __ldg(ip + 4);
         const float3 oo = transform_point(wo, M);  // Ray.Transform (Ray.fs:19-22)
         const float3 od = transform_dir(f3(wdx, wdy, wdz), M);
         if (fbits(m2.y)) {
@@ -506,7 +556,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
           } else {
             // MeshPrimitive pops BLAS node 0 and tests its bounds first (Mesh.fs:224-227)
             const Slab s = slab<true>(f3(m0.x, m0.y, m0.z), f3(m1.x, m1.y, m1.z), o, inv);
-            if (slab_pass<true>(s, t)) cur = fbits(m0.w);
+            if (slab_pass<true>(s, t)) cur = blas_root;
             else pop();
           }
         }

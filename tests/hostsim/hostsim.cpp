@@ -34,6 +34,8 @@ void* hs_scene_create(const BnSceneDesc* desc) {
   d.inst_o2w = cs.inst_o2w.data(); d.meshes = cs.meshes.data(); d.tris = cs.tris.data(); d.alias = cs.alias.data();
   d.sphere_radii = cs.sphere_radii.data(); d.materials = cs.materials.data(); d.lights = cs.lights.data(); d.light_inst = cs.light_inst.data();
   d.flat_tlas = nullptr;  // the ordered scan belongs to traverse_persistent; the per-lane walk uses the tree
+  d.wide = nullptr;       // ... and so do the 4-wide nodes
+  d.tlas_wroot = 0;
   d.tlas = cs.tlas;
   d.n_inst = (uint32_t)cs.inst_head.size();
   d.n_light_inst = (uint32_t)cs.light_inst.size();

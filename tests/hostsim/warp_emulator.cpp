@@ -71,8 +71,9 @@ struct Job {
 Job g_job;
 
 void lane_main(int lane) {
-  if (g_job.any) bn::traverse_persistent<true>(*g_job.sc, *g_job.io, g_job.cold + lane, kLanes);
-  else bn::traverse_persistent<false>(*g_job.sc, *g_job.io, g_job.cold + lane, kLanes);
+  const bool wide = g_job.sc->wide != nullptr;   // as launch_traverse (kernels.cu)
+  if (g_job.any) { if (wide) bn::traverse_persistent<true, true>(*g_job.sc, *g_job.io, g_job.cold + lane, kLanes); else bn::traverse_persistent<true, false>(*g_job.sc, *g_job.io, g_job.cold + lane, kLanes); }
+  else { if (wide) bn::traverse_persistent<false, true>(*g_job.sc, *g_job.io, g_job.cold + lane, kLanes); else bn::traverse_persistent<false, false>(*g_job.sc, *g_job.io, g_job.cold + lane, kLanes); }
   g_warp->done[lane] = true;
   swapcontext(&g_warp->lane[lane], &g_warp->scheduler);
 }
@@ -138,15 +139,20 @@ extern "C" {
 static std::string g_err;
 const char* hsw_last_error(void) { return g_err.c_str(); }
 
+// use_flat_tlas: bit 0 = the small-TLAS ordered scan (as bn_scene_create without BN_NO_FLAT_TLAS); bit 1 = binary nodes (BN_BINARY_NODES)
 void* hsw_scene_create(const BnSceneDesc* desc, int use_flat_tlas) {
   auto* s = new HsWarpScene();
   if (!bnconv::convert_scene(*desc, s->cs, g_err)) { delete s; return nullptr; }
+  if (use_flat_tlas & 2) bnconv::use_binary_nodes(s->cs);
+  use_flat_tlas &= 1;
   bn::DScene& d = s->d;
   const bnconv::ConvertedScene& cs = s->cs;
   d.nodes = cs.nodes.data(); d.inst_trav = cs.inst_trav.data(); d.inst_head = cs.inst_head.data(); d.inst_w2o = cs.inst_w2o.data();
   d.inst_o2w = cs.inst_o2w.data(); d.meshes = cs.meshes.data(); d.tris = cs.tris.data(); d.alias = cs.alias.data();
   d.sphere_radii = cs.sphere_radii.data(); d.materials = cs.materials.data(); d.lights = cs.lights.data(); d.light_inst = cs.light_inst.data();
   d.flat_tlas = (use_flat_tlas && !cs.flat_tlas.empty()) ? cs.flat_tlas.data() : nullptr;  // as bn_scene_create (BN_NO_FLAT_TLAS switches it off)
+  d.wide = cs.wide.empty() ? nullptr : cs.wide.data();
+  d.tlas_wroot = cs.tlas_wroot;
   d.tlas = cs.tlas;
   d.n_inst = (uint32_t)cs.inst_head.size();
   d.n_light_inst = (uint32_t)cs.light_inst.size();
@@ -154,6 +160,7 @@ void* hsw_scene_create(const BnSceneDesc* desc, int use_flat_tlas) {
   d.cam = cs.cam;
   return s;
 }
+int hsw_has_wide(void* h) { return static_cast<HsWarpScene*>(h)->d.wide != nullptr; }
 void hsw_scene_destroy(void* h) { delete static_cast<HsWarpScene*>(h); }
 int hsw_has_flat_tlas(void* h) { return static_cast<HsWarpScene*>(h)->d.flat_tlas != nullptr; }
 

@@ -276,12 +276,13 @@ def warp(root):
 
 @pytest.fixture(scope="module")
 def warp_any_unordered(root):
-    """The same loop built with the default-off experiment -DBN_EXP_ANY_UNORDERED."""
-    return _build_warp_emulator(root, "_any_unordered", ["BN_EXP_ANY_UNORDERED"])
+    """The same loop built with -DBN_ANY_UNORDERED=0: shadow rays walk front to back like closest-hit rays (the default since
+    round 2 is the unordered any-hit walk, adopted after its A/B on the B200)."""
+    return _build_warp_emulator(root, "_any_ordered", ["BN_ANY_UNORDERED=0"])
 
 
-def _warp_trace(lib, scene, rays, any_hit, flat=True):
-    h = lib.hsw_scene_create(C.cast(scene.desc, C.c_void_p), 1 if flat else 0)
+def _warp_trace(lib, scene, rays, any_hit, flat=True, binary=False):
+    h = lib.hsw_scene_create(C.cast(scene.desc, C.c_void_p), (1 if flat else 0) | (2 if binary else 0))
     assert h, lib.hsw_last_error()
     try:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
@@ -293,7 +294,7 @@ def _warp_trace(lib, scene, rays, any_hit, flat=True):
         lib.hsw_scene_destroy(h)
 
 
-def _check_persistent_loop(lib, scene, n_random, seed, flat=True):
+def _check_persistent_loop(lib, scene, n_random, seed, flat=True, binary=False):
     desc = scene.desc.contents
     oracle = OracleScene(scene.desc)
     batches = [("primary", oracle.primary_rays(make_params(32, 24, 1))), ("random", random_rays(scene, n_random, seed=seed)),
@@ -302,7 +303,7 @@ def _check_persistent_loop(lib, scene, n_random, seed, flat=True):
     used_flat = False
     for label, rays in batches:
         want = oracle.trace(rays)
-        got, rendezvous, deferred, used_flat = _warp_trace(lib, scene, rays, False, flat)
+        got, rendezvous, deferred, used_flat = _warp_trace(lib, scene, rays, False, flat, binary)
         _same_hits(desc, got, want)
         if label == "adversarial":
             assert deferred > 0                                            # the NaN-lane rays went through the exact path
@@ -311,28 +312,42 @@ def _check_persistent_loop(lib, scene, n_random, seed, flat=True):
         tm = rays.copy()
         tm["tmax"] = np.where(want["instance"] >= 0, want["t"] * np.float32(1.5), np.float32(50.0))
         tm["tmax"][::2] = np.where(want["instance"][::2] >= 0, want["t"][::2] * np.float32(0.5), np.float32(5.0))
-        got_any = _warp_trace(lib, scene, tm, True, flat)[0]["instance"]
+        got_any = _warp_trace(lib, scene, tm, True, flat, binary)[0]["instance"]
         assert np.array_equal(got_any, oracle.trace(tm, any_hit=True)["instance"])
     return used_flat
 
 
-@pytest.mark.parametrize("name,flat", [("cbox_pt", True), ("cbox_pt", False), ("cbox_bunny", True), ("material_sweep", True), ("bunny_instanced_small", True)])
-def test_persistent_traversal_loop_on_an_emulated_warp_equals_the_oracle(warp, scene_loader, name, flat):
+@pytest.mark.parametrize("binary", [False, True])
+@pytest.mark.parametrize("name,flat", [("cbox_pt", True), ("cbox_pt", False), ("cbox_bunny", True), ("cbox_bunny", False), ("material_sweep", True), ("bunny_instanced_small", True)])
+def test_persistent_traversal_loop_on_an_emulated_warp_equals_the_oracle(warp, scene_loader, name, flat, binary):
     """traverse_persistent as written — phase votes, stay loops, refill, small-TLAS scan (the two Cornell-box scenes; also with
-    the scan switched off), identity-instance shortcut, deferral — run by 32 fibers in lock step: same hits as the oracle."""
-    used_flat = _check_persistent_loop(warp, scene_loader(name), 3000, seed=41, flat=flat)
+    the scan switched off), identity-instance shortcut, deferral — run by 32 fibers in lock step: same hits as the oracle.
+    binary = False: the 4-wide nodes (the default fast path); True: the binary two-box nodes (BN_BINARY_NODES)."""
+    used_flat = _check_persistent_loop(warp, scene_loader(name), 3000, seed=41, flat=flat, binary=binary)
     assert used_flat == (flat and name in ("cbox_pt", "cbox_bunny"))
 
 
-@pytest.mark.parametrize("seed,n_instances", [(51, 3), (52, 16), (53, 17), (54, 120)])
-def test_persistent_traversal_loop_on_randomised_scenes(warp, lib, seed, n_instances):
+@pytest.mark.parametrize("binary", [False, True])
+@pytest.mark.parametrize("seed,n_instances", [(51, 3), (52, 16), (53, 17), (54, 120), (55, 300)])
+def test_persistent_traversal_loop_on_randomised_scenes(warp, lib, seed, n_instances, binary):
     rng = np.random.default_rng(seed)
-    _check_persistent_loop(warp, Scene.LoadString(_random_scene_json(rng, n_instances)), 2000, seed=seed)
+    _check_persistent_loop(warp, Scene.LoadString(_random_scene_json(rng, n_instances)), 2000, seed=seed, binary=binary)
+
+
+def test_wide_nodes_are_really_used(warp, scene_loader, lib):
+    """The default conversion yields 4-wide nodes for every modelled scene (so the tests above exercise them), and the
+    A/B switch really drops them."""
+    warp.hsw_has_wide.argtypes = [C.c_void_p]
+    for name in ("cbox_pt", "cbox_bunny", "material_sweep", "bunny_instanced_small"):
+        for flag, want in ((1, 1), (3, 0)):
+            h = warp.hsw_scene_create(C.cast(scene_loader(name).desc, C.c_void_p), flag)
+            assert h and warp.hsw_has_wide(h) == want, name
+            warp.hsw_scene_destroy(h)
 
 
 def test_unordered_any_hit_experiment_gives_the_same_answers(warp_any_unordered, scene_loader, lib):
-    """-DBN_EXP_ANY_UNORDERED: shadow rays walk left-first whatever the ray direction; occlusion answers (and, untouched,
-    the closest hits) stay the oracle's."""
+    """Shadow rays walk left-first whatever the ray direction by default (BN_ANY_UNORDERED=1; covered by every other test of
+    this file); with the front-to-back any-hit walk (-DBN_ANY_UNORDERED=0) the occlusion answers are the same oracle's."""
     for name in ("cbox_bunny", "material_sweep", "bunny_instanced_small"):
         _check_persistent_loop(warp_any_unordered, scene_loader(name), 2500, seed=61)
     _check_persistent_loop(warp_any_unordered, Scene.LoadString(_random_scene_json(np.random.default_rng(62), 40)), 2000, seed=62)
