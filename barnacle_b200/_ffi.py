@@ -19,6 +19,7 @@ BN_MAT_LAMBERTIAN, BN_MAT_MIRROR, BN_MAT_DIELECTRIC, BN_MAT_PBR = 0, 1, 2, 3
 BN_CAM_PINHOLE, BN_CAM_THIN_LENS = 0, 1
 BN_INTEGRATOR_PATH_TRACING, BN_INTEGRATOR_DIRECT, BN_INTEGRATOR_NORMAL = 0, 1, 2
 BN_MLT_GAUSSIAN, BN_MLT_KELEMEN = 0, 1
+BN_PARTITION_AUTO, BN_PARTITION_SAMPLE, BN_PARTITION_TILE = 0, 1, 2
 BN_RENDER_TRACE_NULL_SHADOW = 1
 BN_RENDER_PROFILE = 2
 BN_RENDER_FORCE_EXACT = 4
@@ -126,6 +127,11 @@ SYMBOLS = {
     "bn_scene_destroy": (None, [_VP]),
     "bn_render": (C.c_int, [_VP, C.POINTER(BnRenderParams), _VP, C.POINTER(BnStats)]),
     "bn_render_device": (C.c_int, [_VP, C.POINTER(BnRenderParams), _VP, _VP, C.POINTER(BnStats)]),
+    "bn_multi_scene_create": (C.c_int, [C.POINTER(BnSceneDesc), C.POINTER(C.c_int32), C.c_int32, C.POINTER(_VP)]),
+    "bn_multi_scene_destroy": (None, [_VP]),
+    "bn_multi_scene_device_count": (C.c_int, [_VP]),
+    "bn_render_multi": (C.c_int, [_VP, C.POINTER(BnRenderParams), C.c_int32, _VP, C.POINTER(BnStats)]),
+    "bn_multi_partition": (C.c_int, [C.POINTER(BnRenderParams), C.c_int32, C.c_int32, C.c_int32, C.POINTER(BnRenderParams), C.POINTER(C.c_int32)]),
     "bn_trace": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int, _VP]),
     "bn_trace_device": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int, _VP, _VP, C.POINTER(C.c_float)]),
     "bn_render_radiance": (C.c_int, [_VP, C.POINTER(BnRenderParams), _VP]),

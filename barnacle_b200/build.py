@@ -28,7 +28,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "-ccbin", HOST_CXX]
 
 HOST_SOURCES = ["host/error.cpp", "host/scene_host.cpp", "cuda/scene_convert.cpp"]
-CUDA_SOURCES = ["cuda/kernels.cu", "cuda/mlt.cu", "cuda/bvh_build.cu"]
+CUDA_SOURCES = ["cuda/kernels.cu", "cuda/mlt.cu", "cuda/bvh_build.cu", "cuda/multi.cu"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

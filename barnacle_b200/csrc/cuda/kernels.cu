@@ -818,13 +818,47 @@ int bn_device_count(void) {
 int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   if (!desc || !out) { bnhost::set_error("bn_scene_create: NULL argument"); return BN_ERR_INVALID; }
   *out = nullptr;
-  int ndev = bn_device_count();
-  if (ndev <= 0) { bnhost::set_error("no CUDA device available (the hot path has no CPU fallback)"); return BN_ERR_NO_DEVICE; }
-  if (device < 0 || device >= ndev) { bnhost::set_error("bn_scene_create: device ordinal out of range"); return BN_ERR_INVALID; }
   bnconv::ConvertedScene cs;
+  int rc = bnint::convert_for_device(desc, cs);
+  if (rc != BN_OK) return rc;
+  return bnint::scene_from_converted(cs, device, out);
+}
+
+}  // extern "C"
+
+// Flattening (host) and upload (device) are separate steps so that a multi-device render flattens ONCE (multi.cu).
+int bnint::convert_for_device(const BnSceneDesc* desc, bnconv::ConvertedScene& cs) {
+  if (bn_device_count() <= 0) { bnhost::set_error("no CUDA device available (the hot path has no CPU fallback)"); return BN_ERR_NO_DEVICE; }
   std::string err;
   if (!bnconv::convert_scene(*desc, cs, err)) { bnhost::set_error(err); return BN_ERR_INVALID; }
   if (std::getenv("BN_BINARY_NODES")) bnconv::use_binary_nodes(cs);  // A/B switch: the binary-node fast path
+  return BN_OK;
+}
+
+// The scene's own device film (grown on demand, parked with the other buffers when the scene dies).
+int bnint::scene_film(BnScene* s, size_t len, float** out) {
+  BN_CUDA(cudaSetDevice(s->device));
+  if (s->film_len < len) {
+    if (s->film) cudaFree(s->film);
+    s->film = nullptr; s->film_len = 0;
+    BN_CUDA(cudaMalloc((void**)&s->film, len * sizeof(float)));
+    s->film_len = len;
+  }
+  *out = s->film;
+  return BN_OK;
+}
+
+int bnint::render_on_stream(BnScene* s, const BnRenderParams* p, float* d_film, cudaStream_t stream, BnStats* stats) {
+  int rc = validate_params(p);
+  if (rc != BN_OK) return rc;
+  return render_waves(s, p, d_film, nullptr, stream, stats);
+}
+
+int bnint::scene_from_converted(const bnconv::ConvertedScene& cs, int device, BnScene** out) {
+  *out = nullptr;
+  const int ndev = bn_device_count();
+  if (ndev <= 0) { bnhost::set_error("no CUDA device available (the hot path has no CPU fallback)"); return BN_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) { bnhost::set_error("bn_scene_create: device ordinal out of range"); return BN_ERR_INVALID; }
   BN_CUDA(cudaSetDevice(device));
   int cc_major = 0, sm_count = 0;  // (cudaGetDeviceProperties costs milliseconds per call; two attributes do not)
   BN_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
@@ -856,6 +890,8 @@ int bn_scene_create(const BnSceneDesc* desc, int device, BnScene** out) {
   return BN_OK;
 }
 
+extern "C" {
+
 void bn_scene_destroy(BnScene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
@@ -882,14 +918,9 @@ int bn_render(BnScene* s, const BnRenderParams* p, float* film, BnStats* stats) 
   if (!s || !film) { bnhost::set_error("bn_render: NULL argument"); return BN_ERR_INVALID; }
   int rc = validate_params(p);
   if (rc != BN_OK) return rc;
-  BN_CUDA(cudaSetDevice(s->device));
   const size_t len = (size_t)p->width * p->height * 3;
-  if (s->film_len < len) {
-    if (s->film) cudaFree(s->film);
-    s->film = nullptr; s->film_len = 0;
-    BN_CUDA(cudaMalloc((void**)&s->film, len * sizeof(float)));
-    s->film_len = len;
-  }
+  float* d_film = nullptr;
+  if ((rc = bnint::scene_film(s, len, &d_film)) != BN_OK) return rc;
   rc = render_waves(s, p, s->film, nullptr, nullptr, stats);
   if (rc != BN_OK) return rc;
   BN_CUDA(cudaMemcpy(film, s->film, len * sizeof(float), cudaMemcpyDeviceToHost));

@@ -46,3 +46,13 @@ struct BnScene {
   std::vector<cudaEvent_t> events;  // BN_RENDER_PROFILE: start/stop pairs, one per kernel launch
 };
 
+
+// Internal entry points shared by kernels.cu and multi.cu (hidden visibility: not part of the C ABI).
+#include "../../../include/barnacle_b200.h"
+#include "scene_convert.h"
+namespace bnint {
+int convert_for_device(const BnSceneDesc* desc, bnconv::ConvertedScene& cs);                    // host: flatten + validate
+int scene_from_converted(const bnconv::ConvertedScene& cs, int device, BnScene** out);           // device: one allocation, one copy
+int scene_film(BnScene* s, size_t len, float** out);                                             // the scene's device film, grown on demand
+int render_on_stream(BnScene* s, const BnRenderParams* p, float* d_film, cudaStream_t stream, BnStats* stats);  // film stays on the device
+}  // namespace bnint

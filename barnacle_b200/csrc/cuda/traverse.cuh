@@ -66,6 +66,9 @@ constexpr int kRefillMinAny = BN_REFILL_MIN_ANY;  // ... for any-hit (shadow) ra
 #ifndef BN_ANY_UNORDERED
 #define BN_ANY_UNORDERED 1
 #endif
+#ifndef BN_WIDE_LDG256
+#define BN_WIDE_LDG256 0   // 1: a 4-wide node is fetched with four 256-bit loads instead of eight 128-bit ones
+#endif
 #ifndef BN_PREFETCH_AHEAD
 #define BN_PREFETCH_AHEAD 16384
 #endif
@@ -89,6 +92,19 @@ __device__ unsigned long long g_trav_stats[24];
 #endif
 
 BN_DEV uint32_t fbits(float f) { return __float_as_uint(f); }
+
+// 32-B load (sm_100: LDG.E.ENL2.256): one L1 sector per lane in ONE request
+struct F8 { float v[8]; };
+#ifndef BN_HOSTSIM
+BN_DEV F8 ldg256(uintptr_t p) {
+  F8 r;
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+  return r;
+}
+#else
+BN_DEV F8 ldg256(uintptr_t p) { F8 r; for (int k = 0; k < 8; ++k) r.v[k] = reinterpret_cast<const float*>(p)[k]; return r; }
+#endif
 
 // Triangle.Intersect — shared arithmetic of both overloads (Mesh.fs:24-82).
 // Returns true and t' (+ u, v) iff the reference would accept against `t`.
@@ -410,12 +426,25 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
             // ---- one 4-wide node (128 B): near / far planes of the four slots picked by the direction signs at the
             // address level, so each box is 6 FADD + 6 FMUL and the two min / max chains of slab<true>
             const uintptr_t nb = reinterpret_cast<uintptr_t>(sc.wide) + (size_t)(cur & kIndexMask) * 128u;
+#if BN_WIDE_LDG256
+            // the whole node in four 32-B loads (one L1 sector each; sm_100's 256-bit LDG), near / far picked by selects
+            const F8 c0 = ldg256(nb), c1 = ldg256(nb + 32u), c2 = ldg256(nb + 64u), c3 = ldg256(nb + 96u);
+            const bool sx = (signs & 1u) != 0u, sy = (signs & 2u) != 0u, sz = (signs & 4u) != 0u;
+            const float4 lx = make_float4(c0.v[0], c0.v[1], c0.v[2], c0.v[3]), ly = make_float4(c0.v[4], c0.v[5], c0.v[6], c0.v[7]);
+            const float4 lz = make_float4(c1.v[0], c1.v[1], c1.v[2], c1.v[3]);
+            const float4 hx = make_float4(c2.v[0], c2.v[1], c2.v[2], c2.v[3]), hy = make_float4(c2.v[4], c2.v[5], c2.v[6], c2.v[7]);
+            const float4 hz = make_float4(c3.v[0], c3.v[1], c3.v[2], c3.v[3]);
+            const float4 nx = sx ? lx : hx, fx = sx ? hx : lx, ny = sy ? ly : hy, fy = sy ? hy : ly, nz = sz ? lz : hz, fz = sz ? hz : lz;
+            const uint4 rf = make_uint4(__float_as_uint(c1.v[4]), __float_as_uint(c1.v[5]), __float_as_uint(c1.v[6]), __float_as_uint(c1.v[7]));
+            const uint32_t flips_word = __float_as_uint(c3.v[4]);
+#else
             // near plane of an axis = lo if dir > 0, else hi (64 B further: bit 6 of the address); far = the other one
             const uintptr_t ax = nb | ((signs & 1u) ? 0u : 64u), ay = nb | ((signs & 2u) ? 0u : 64u), az = nb | ((signs & 4u) ? 0u : 64u);
             const float4 nx = __ldg(reinterpret_cast<const float4*>(ax)), fx = __ldg(reinterpret_cast<const float4*>(ax ^ 64u));
             const float4 ny = __ldg(reinterpret_cast<const float4*>(ay) + 1), fy = __ldg(reinterpret_cast<const float4*>(ay ^ 64u) + 1);
             const float4 nz = __ldg(reinterpret_cast<const float4*>(az) + 2), fz = __ldg(reinterpret_cast<const float4*>(az ^ 64u) + 2);
             const uint4 rf = __ldg(reinterpret_cast<const uint4*>(nb) + 3);
+#endif
             // slab<true> + slab_pass<true> per slot; key = entry distance if the slot passes, else -1 (an entry distance is >= 1e-3)
 #define BN_WIDE_SLOT(c)                                                                                                         \
             fmaxf(fmaxf(1e-3f, (nx.c - o.x) * inv.x), fmaxf((ny.c - o.y) * inv.y, (nz.c - o.z) * inv.z)) <=                      \
@@ -429,7 +458,11 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
             // dir[axis_L] > 0, slot 2 before 3 iff dir[axis_R] > 0 (BVH.fs:51-56 / Mesh.fs:235-240 applied twice) — tabulated
             // per direction octant in the node.  An any-hit query returns the same boolean whatever the order.
             if (!ANY || !BN_ANY_UNORDERED) {
+#if BN_WIDE_LDG256
+              const uint32_t fl = flips_word >> ((signs & 7u) * 3u);
+#else
               const uint32_t fl = __ldg(reinterpret_cast<const uint32_t*>(nb) + 28) >> ((signs & 7u) * 3u);
+#endif
               if (fl & 1u) { const uint32_t r = r0; r0 = r1; r1 = r; const float k = k0; k0 = k1; k1 = k; }
               if (fl & 2u) { const uint32_t r = r2; r2 = r3; r3 = r; const float k = k2; k2 = k3; k3 = k; }
               if (fl & 4u) {

@@ -176,6 +176,43 @@ class GpuScene:
         return ms.value
 
 
+class MultiGpuScene:
+    """The scene on several devices behind ONE C-ABI handle (bn_multi_scene_create): flattened once, uploaded to every device
+    by its own host thread.  `render` is bn_render_multi — the drop-in for Integrator.Render on a multi-GPU box: the
+    (pixel, sampleId) space is shared out inside the call, the films are combined over NVLink on devices[0]."""
+
+    def __init__(self, desc_ptr, devices):
+        self._lib = _ffi.load()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        check(self._lib.bn_multi_scene_create(desc_ptr, arr, len(self.devices), C.byref(h)), "bn_multi_scene_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bn_multi_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def render(self, params: BnRenderParams, film: np.ndarray | None = None, partition: int = _ffi.BN_PARTITION_AUTO):
+        if film is None:
+            film = np.empty((params.height * params.width, 3), dtype=np.float32)
+        assert film.dtype == np.float32 and film.flags["C_CONTIGUOUS"] and film.size == params.height * params.width * 3
+        st = BnStats()
+        check(self._lib.bn_render_multi(self._h, C.byref(params), partition, film.ctypes.data, C.byref(st)), "bn_render_multi")
+        return film, GpuScene._stats(st)
+
+
+def multi_partition(params: BnRenderParams, partition: int, n_devices: int, rank: int):
+    """(share of device `rank`, empty?) as bn_render_multi computes it (host logic; needs no GPU)."""
+    out, empty = BnRenderParams(), C.c_int32(0)
+    check(_ffi.load().bn_multi_partition(C.byref(params), partition, n_devices, rank, C.byref(out), C.byref(empty)), "bn_multi_partition")
+    return out, bool(empty.value)
+
+
 class GpuPathTracingIntegrator:
     """Drop-in for PathTracingIntegrator (PathTracing.fs:9-12) whose Render
     (Integrator.fs:46-55) runs on the GPU.  `kind` selects the Li variant:

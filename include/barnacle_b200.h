@@ -236,6 +236,31 @@ BN_API int bn_render(BnScene* scene, const BnRenderParams* params, float* film_r
 BN_API int bn_render_device(BnScene* scene, const BnRenderParams* params, void* d_film_rgb,
                             void* cuda_stream, BnStats* stats);
 
+/* ---- several devices behind one call ---------------------------------------------------------
+ * In the reference the whole machine's parallelism lives INSIDE Integrator.Render (Base/Integrator.fs:46-55: 16x16
+ * tiles over the TPL pool, called once from Extensions/Scene/Render.fs:15-17), so the drop-in fans out over the GPUs of
+ * the box from inside the call as well.  bn_multi_scene_create flattens the scene once and uploads it to every listed
+ * device (one host thread each; the same ordinal may be listed twice); bn_render_multi renders each device's share of
+ * the (pixel, sampleId) space and combines the films on devices[0] with one kernel that reads the other devices' films
+ * over NVLink (peer access; a staged peer copy where there is none), adding them in the order of the list — the same
+ * film every run.  No NCCL / torch involved.  film_rgb: HOST pointer, W*H*3 floats, Film.Pixels layout. */
+typedef struct BnMultiScene BnMultiScene;
+enum {
+  BN_PARTITION_AUTO = 0,   /* sample split when the window has at least as many samples as devices, else tile split */
+  BN_PARTITION_SAMPLE = 1, /* device g renders sampleIds [b + g*n/G, b + (g+1)*n/G) of every pixel, weight 1/spp: the same sample set as
+                              one device; the per-pixel sum is re-associated (fp32 rounding only) */
+  BN_PARTITION_TILE = 2    /* device g renders the 16-pixel tile rows g, g+G, ... (Integrator.fs:16 tile size): disjoint pixels, bit-identical
+                              to one device */
+};
+BN_API int bn_multi_scene_create(const BnSceneDesc* desc, const int32_t* devices, int32_t n_devices, BnMultiScene** out);
+BN_API void bn_multi_scene_destroy(BnMultiScene* scene);
+BN_API int bn_multi_scene_device_count(const BnMultiScene* scene);
+/* stats (may be NULL): rays / paths / launches summed over the devices; gpu_ms = the slowest device + the combine. */
+BN_API int bn_render_multi(BnMultiScene* scene, const BnRenderParams* params, int32_t partition, float* film_rgb, BnStats* stats);
+/* The share device `rank` of `n_devices` renders (host logic only, no device needed): *out = params restricted to it,
+ * *empty = 1 when the share holds no path. */
+BN_API int bn_multi_partition(const BnRenderParams* params, int32_t partition, int32_t n_devices, int32_t rank, BnRenderParams* out, int32_t* empty);
+
 /* Fixed-batch traversal entry (parity tests, microbenchmarks).
  * any_hit = 0: PrimitiveAggregate.Intersect/3 (Extensions/Aggregate/BVH.fs:37-58)
  * any_hit = 1: PrimitiveAggregate.Intersect/2 (Extensions/Aggregate/BVH.fs:11-35)
