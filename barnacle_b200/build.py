@@ -66,17 +66,23 @@ def _build(force: bool, verbose: bool, stats: bool, defines: list[str], LIB: str
     if not force and _newer(LIB, _all_inputs()):
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
-    objs = []
+    objs, cmds = [], []
+    dflags = ["-D" + d for d in defines]   # host and device code share switches such as BN_NET9_FMA
     for src in HOST_SOURCES:
         obj = os.path.join(OBJ_DIR, src.replace("/", "_") + ".o")
-        cmd = [HOST_CXX, *HOST_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-        _run(cmd, verbose)
+        cmds.append([HOST_CXX, *HOST_FLAGS, *dflags, "-c", os.path.join(CSRC, src), "-o", obj])
         objs.append(obj)
     for src in CUDA_SOURCES:
         obj = os.path.join(OBJ_DIR, src.replace("/", "_") + ".o")
-        cmd = [NVCC, *NVCC_FLAGS, *(["-DBN_TRAV_STATS"] if stats else []), *["-D" + d for d in defines], *(["-Xptxas", "-v"] if verbose else []), "-c", os.path.join(CSRC, src), "-o", obj]
-        _run(cmd, verbose)
+        cmds.append([NVCC, *NVCC_FLAGS, *(["-DBN_TRAV_STATS"] if stats else []), *dflags, *(["-Xptxas", "-v"] if verbose else []), "-c", os.path.join(CSRC, src), "-o", obj])
         objs.append(obj)
+    if verbose:
+        for cmd in cmds:
+            _run(cmd, verbose)
+    else:  # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda c: _run(c, False), cmds))
     cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-cudart", "static"]
     _run(cmd, verbose)
     if not with_cli:

@@ -45,6 +45,18 @@ static_assert(sizeof(GNode) == 64, "GNode must be 64 B");
 // Planes are stored per axis for the four slots (SoA), so that the near / far plane of an axis is ONE 16-B load whose
 // address depends on the sign of the ray direction — no min / max / select per box: the hi planes sit 64 B after the lo
 // planes, so "near" / "far" is bit 6 of the address (the array is 128-B aligned).
+// BN_WIDE_SWIZZLE (compile-time, default off): in memory the eight 16-B chunks of node i are XOR-swizzled — logical chunk j
+// sits at physical chunk j ^ (i & 7).  All lanes of a warp read the SAME logical chunk of DIFFERENT nodes at once, and the
+// L1 data array serves one lane per cycle when every lane's 16 bytes sit at the same offset of their 128-B lines
+// (profiles/r02_l1_gather_microbench.txt: 8 x LDG.128 of random 128-B records run at one lane-load per cycle per SM
+// whatever the number of active lanes); the swizzle spreads a warp's loads over the eight bank groups.  Measured on the
+// B200 (profiles/r02_ab_session4_swizzle.log): the L1 data pipe of the extend launches falls from 80-83 % to 74-75 % busy —
+// and the frame time does not move (C1 -1.0 %, C2 -1.4 %, C3 +0.8 %, C4 +1.8 %): the kernel is bound by instruction issue
+// (76 %), not by L1, and the swizzle costs two instructions per node step.  Kept as a switch; the struct below is the
+// LOGICAL layout.
+#ifndef BN_WIDE_SWIZZLE
+#define BN_WIDE_SWIZZLE 0
+#endif
 struct __align__(128) GWide {
   float lo[3][4];    //   +0: lo.x of slots 0..3 | +16: lo.y | +32: lo.z
   uint32_t ref[4];   //  +48: child refs (same encoding as GNode.left / right; interior = ABSOLUTE GWide index)

@@ -378,6 +378,13 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
     }
     for (uint32_t i = 0; i < d.instance_count; ++i)
       out.inst_trav[i].wroot = out.wide.empty() ? out.inst_trav[i].root : out.inst_wroot[i];
+    // Bank swizzle (device_scene.h: kWideSwizzle): node i keeps its logical 16-B chunk j at physical chunk j ^ (i & 7)
+    for (size_t i = 0; BN_WIDE_SWIZZLE && i < out.wide.size(); ++i) {
+      const bn::GWide lg = out.wide[i];
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(&lg);
+      unsigned char* dst = reinterpret_cast<unsigned char*>(&out.wide[i]);
+      for (unsigned j = 0; j < 8; ++j) std::memcpy(dst + 16u * (j ^ (unsigned)(i & 7u)), src + 16u * j, 16);
+    }
   }
   // Small-TLAS ordered scan (traverse.cuh): instance order of the reference's walk for each octant.
   // The walk visits left first iff dir[splitAxis] > 0 (Aggregate/BVH.fs:51-56) and leaf items in

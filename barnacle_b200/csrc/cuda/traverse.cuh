@@ -428,7 +428,20 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
             const uintptr_t nb = reinterpret_cast<uintptr_t>(sc.wide) + (size_t)(cur & kIndexMask) * 128u;
 #if BN_WIDE_LDG256
             // the whole node in four 32-B loads (one L1 sector each; sm_100's 256-bit LDG), near / far picked by selects
-            const F8 c0 = ldg256(nb), c1 = ldg256(nb + 32u), c2 = ldg256(nb + 64u), c3 = ldg256(nb + 96u);
+            // (swizzled chunks: a 32-B pair {2k, 2k+1} stays a pair under the XOR, with its halves exchanged when bit 0 of the swizzle is set)
+            const uint32_t swz32 = BN_WIDE_SWIZZLE ? (cur & 6u) << 4 : 0u;
+            const bool swap_halves = BN_WIDE_SWIZZLE && (cur & 1u) != 0u;
+            F8 c0 = ldg256(nb | swz32), c1 = ldg256(nb | (swz32 ^ 32u)), c2 = ldg256(nb | (swz32 ^ 64u)), c3 = ldg256(nb | (swz32 ^ 96u));
+            if (swap_halves) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float tq;
+                tq = c0.v[q]; c0.v[q] = c0.v[q + 4]; c0.v[q + 4] = tq;
+                tq = c1.v[q]; c1.v[q] = c1.v[q + 4]; c1.v[q + 4] = tq;
+                tq = c2.v[q]; c2.v[q] = c2.v[q + 4]; c2.v[q + 4] = tq;
+                tq = c3.v[q]; c3.v[q] = c3.v[q + 4]; c3.v[q + 4] = tq;
+              }
+            }
             const bool sx = (signs & 1u) != 0u, sy = (signs & 2u) != 0u, sz = (signs & 4u) != 0u;
             const float4 lx = make_float4(c0.v[0], c0.v[1], c0.v[2], c0.v[3]), ly = make_float4(c0.v[4], c0.v[5], c0.v[6], c0.v[7]);
             const float4 lz = make_float4(c1.v[0], c1.v[1], c1.v[2], c1.v[3]);
@@ -438,12 +451,15 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
             const uint4 rf = make_uint4(__float_as_uint(c1.v[4]), __float_as_uint(c1.v[5]), __float_as_uint(c1.v[6]), __float_as_uint(c1.v[7]));
             const uint32_t flips_word = __float_as_uint(c3.v[4]);
 #else
-            // near plane of an axis = lo if dir > 0, else hi (64 B further: bit 6 of the address); far = the other one
-            const uintptr_t ax = nb | ((signs & 1u) ? 0u : 64u), ay = nb | ((signs & 2u) ? 0u : 64u), az = nb | ((signs & 4u) ? 0u : 64u);
-            const float4 nx = __ldg(reinterpret_cast<const float4*>(ax)), fx = __ldg(reinterpret_cast<const float4*>(ax ^ 64u));
-            const float4 ny = __ldg(reinterpret_cast<const float4*>(ay) + 1), fy = __ldg(reinterpret_cast<const float4*>(ay ^ 64u) + 1);
-            const float4 nz = __ldg(reinterpret_cast<const float4*>(az) + 2), fz = __ldg(reinterpret_cast<const float4*>(az ^ 64u) + 2);
-            const uint4 rf = __ldg(reinterpret_cast<const uint4*>(nb) + 3);
+            // near plane of an axis = lo if dir > 0, else hi (64 B further: bit 6 of the offset); far = the other one.  The
+            // node's 16-B chunks are XOR-swizzled by its index (device_scene.h), so that the lanes of a warp, which all
+            // read the same logical chunk of different nodes, hit different L1 bank groups: offset = logical ^ swz
+            const uint32_t swz = BN_WIDE_SWIZZLE ? (cur & 7u) << 4 : 0u;
+            const uint32_t mx = swz ^ ((signs & 1u) ? 0u : 64u), my = swz ^ ((signs & 2u) ? 16u : 80u), mz = swz ^ ((signs & 4u) ? 32u : 96u);
+            const float4 nx = __ldg(reinterpret_cast<const float4*>(nb | mx)), fx = __ldg(reinterpret_cast<const float4*>(nb | (mx ^ 64u)));
+            const float4 ny = __ldg(reinterpret_cast<const float4*>(nb | my)), fy = __ldg(reinterpret_cast<const float4*>(nb | (my ^ 64u)));
+            const float4 nz = __ldg(reinterpret_cast<const float4*>(nb | mz)), fz = __ldg(reinterpret_cast<const float4*>(nb | (mz ^ 64u)));
+            const uint4 rf = __ldg(reinterpret_cast<const uint4*>(nb | (swz ^ 48u)));
 #endif
             // slab<true> + slab_pass<true> per slot; key = entry distance if the slot passes, else -1 (an entry distance is >= 1e-3)
 #define BN_WIDE_SLOT(c)                                                                                                         \
@@ -461,7 +477,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
 #if BN_WIDE_LDG256
               const uint32_t fl = flips_word >> ((signs & 7u) * 3u);
 #else
-              const uint32_t fl = __ldg(reinterpret_cast<const uint32_t*>(nb) + 28) >> ((signs & 7u) * 3u);
+              const uint32_t fl = __ldg(reinterpret_cast<const uint32_t*>(nb | (swz ^ 112u))) >> ((signs & 7u) * 3u);
 #endif
               if (fl & 1u) { const uint32_t r = r0; r0 = r1; r1 = r; const float k = k0; k0 = k1; k1 = k; }
               if (fl & 2u) { const uint32_t r = r2; r2 = r3; r3 = r; const float k = k2; k2 = k3; k3 = k; }

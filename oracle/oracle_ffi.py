@@ -13,7 +13,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbarnacle_oracle.so")
+# BN_NET9_FMA=0 in the environment selects the restatement built without .NET 9's fused Cross / Transform (Makefile)
+_FMA0 = os.environ.get("BN_NET9_FMA") == "0"
+LIB_NAME = "libbarnacle_oracle_fma0.so" if _FMA0 else "libbarnacle_oracle.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("tmax", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("instance", "<i4"), ("primitive", "<i4")])
@@ -26,7 +29,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "barnacle_oracle.cpp")
     deps = [src, os.path.join(_HERE, "..", "include", "barnacle_b200.h"), os.path.join(_HERE, "..", "include", "bn_portable_math.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
-        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", LIB_NAME], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return LIB_PATH
 
 

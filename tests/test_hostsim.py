@@ -353,6 +353,16 @@ def test_unordered_any_hit_experiment_gives_the_same_answers(warp_any_unordered,
     _check_persistent_loop(warp_any_unordered, Scene.LoadString(_random_scene_json(np.random.default_rng(62), 40)), 2000, seed=62)
 
 
+@pytest.mark.parametrize("tag,defines", [("_swz", ["BN_WIDE_SWIZZLE=1"]), ("_swz256", ["BN_WIDE_SWIZZLE=1", "BN_WIDE_LDG256=1"]), ("_ldg256", ["BN_WIDE_LDG256=1"])])
+def test_wide_node_layout_switches_give_the_same_hits(root, scene_loader, lib, tag, defines):
+    """The bank-swizzled node layout (-DBN_WIDE_SWIZZLE=1: chunk j of node i at j ^ (i & 7), converter and kernel agree) and the
+    256-bit node fetch (-DBN_WIDE_LDG256=1), measured on the B200 and left off: same hits, same any-hit answers."""
+    variant = _build_warp_emulator(root, tag, defines)
+    for name in ("cbox_bunny", "material_sweep", "bunny_instanced_small"):
+        _check_persistent_loop(variant, scene_loader(name), 2500, seed=91)
+    _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(92), 120)), 2000, seed=92)
+
+
 def test_stay_refill_experiment_gives_the_same_hits(root, scene_loader, lib):
     """-DBN_EXP_STAY_REFILL=14: a different moment to leave the stay loops, the same hits."""
     variant = _build_warp_emulator(root, "_stay_refill", ["BN_EXP_STAY_REFILL=14"])
