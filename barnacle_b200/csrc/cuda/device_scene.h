@@ -114,6 +114,10 @@ static_assert(sizeof(GInstHead) == 48, "GInstHead must be 48 B");
 // Small-TLAS fast path: for each of the 8 direction octants, the instances in the
 // order the reference's TLAS walk reaches them (the order depends only on the signs
 // of the ray direction), each with its world AABB: 32 B per entry.
+// The box is stored as the octant's NEAR planes (bmin[a] = world min if dir[a] > 0 in this octant, else world max) and
+// FAR planes (bmax): with lo <= hi, finite operands and a finite non-zero 1/d of that sign, (near - o) * inv is exactly
+// Min(t0, t1) and (far - o) * inv exactly Max(t0, t1) of the reference's slab test (monotone rounding), up to the sign
+// of a zero, which the Max with 1e-3 / the comparison against tMin >= 1e-3 cannot see.
 struct __align__(16) GFlatInst {
   float bmin[3]; uint32_t slot;
   float bmax[3]; uint32_t direct_root;  // identity mesh instance: its BLAS root ref (the scan enters it without phase E); else 0xFFFFFFFF

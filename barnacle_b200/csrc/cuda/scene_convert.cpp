@@ -412,7 +412,13 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
       for (uint32_t k = 0; k < d.instance_count; ++k) {
         bn::GFlatInst& f = out.flat_tlas[(size_t)oct * d.instance_count + k];
         const BnInstance& in = d.instances[order[k]];
-        std::memcpy(f.bmin, in.bounds_min, 12); std::memcpy(f.bmax, in.bounds_max, 12);
+        // near / far plane per axis for THIS octant (bit a of oct = dir[a] > 0: near = min): the scan's slab test needs no
+        // min / max per axis — same values as Min/MaxNative(t0, t1) for every ray the fast path takes (device_scene.h)
+        for (int a = 0; a < 3; ++a) {
+          const bool pos = ((oct >> a) & 1u) != 0u;
+          f.bmin[a] = pos ? in.bounds_min[a] : in.bounds_max[a];
+          f.bmax[a] = pos ? in.bounds_max[a] : in.bounds_min[a];
+        }
         f.slot = order[k];
         f.direct_root = out.inst_trav[order[k]].identity ? out.inst_trav[order[k]].wroot : 0xFFFFFFFFu;  // (use_binary_nodes() re-points it)
       }

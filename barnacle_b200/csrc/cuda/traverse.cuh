@@ -145,6 +145,13 @@ BN_DEV int sphere_test(float radius, float3 o, float3 d, float t, float& tp) {
 // bit a set iff d[a] > 0; bit 3 always set (GNode.axis == 3: "always left first")
 BN_DEV uint32_t dir_signs(float3 d) { return (d.x > 0.f ? 1u : 0u) | (d.y > 0.f ? 2u : 0u) | (d.z > 0.f ? 4u : 0u) | 8u; }
 
+// slab<true> + slab_pass<true> on a GFlatInst, whose planes are already sorted into near (a) / far (b) for the ray's octant
+BN_DEV bool flat_pass(const float4 a, const float4 b, const float3 o, const float3 inv, const float t) {
+  const float tn = fmaxf(fmaxf(1e-3f, (a.x - o.x) * inv.x), fmaxf((a.y - o.y) * inv.y, (a.z - o.z) * inv.z));
+  const float tf = fminf((b.x - o.x) * inv.x, fminf((b.y - o.y) * inv.y, (b.z - o.z) * inv.z));
+  return tn <= fminf(t, tf);
+}
+
 struct TraceResult {
   bool hit;
   float t;
@@ -396,7 +403,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
           for (uint32_t k = 0; k < n_inst; ++k) {
             BN_WORK(25);
             const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
-            if (slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) mask |= 1u << k;
+            if (flat_pass(a, b, wo, winv, t)) mask |= 1u << k;
           }
           tl_pos = mask;
           if (mask) cur = kScan;
@@ -625,7 +632,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
           tl_pos &= tl_pos - 1u;
           BN_WORK(30);
           const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
-          if (ANY || slab_pass<true>(slab<true>(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), wo, winv), t)) {
+          if (ANY || flat_pass(a, b, wo, winv, t)) {
 #ifdef BN_EXP_SCAN_LEAF
             // experiment queued for the next GPU session (default off; found on the warp emulator): an identity
             // mesh instance whose whole BLAS is ONE leaf (the Cornell-box walls: two triangles) is tested right here, in slot

@@ -184,6 +184,26 @@ module Native =
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int bn_render_pssmlt(nativeint scene, BnMltParams& p, nativeint filmRgb, BnMltStats& stats)
 
+    /// Several devices behind one call (include/barnacle_b200.h): the scene is flattened once and uploaded to every listed
+    /// device; bn_render_multi shares the (pixel, sampleId) space out inside the call — Integrator.Render's own parallelism
+    /// (Integrator.fs:46-55) on the GPUs of the box instead of the TPL pool — and combines the films over NVLink on devices[0].
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int bn_multi_scene_create(BnSceneDesc& desc, nativeint devices, int nDevices, nativeint& scene)
+
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern void bn_multi_scene_destroy(nativeint scene)
+
+    /// partition: 0 auto (sample split when there are at least as many samples as devices, else tile rows), 1 sample, 2 tile
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int bn_render_multi(nativeint scene, BnRenderParams& p, int partition, nativeint filmRgb, BnStats& stats)
+
+    /// Parity entry points (integration/fsharp/ParityDump.fs): fixed ray batches and per-path radiance.
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int bn_trace(nativeint scene, nativeint rays, uint64 n, int anyHit, nativeint hits)
+
+    [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
+    extern int bn_render_radiance(nativeint scene, BnRenderParams& p, nativeint radiance)
+
     /// BVHNode.Build on the device (optional, "next" row N2): same nodes and permutation as Util/BVH.fs:239-247, byte for byte.
     [<DllImport(Lib, CallingConvention = CallingConvention.Cdecl)>]
     extern int bn_bvh_build(int device, nativeint boxes, uint32 n, nativeint nodes, uint32 maxNodes, nativeint perm, nativeint ms)
@@ -245,8 +265,8 @@ module GpuScene =
     /// `original`: Scene.Traverse(t) in its original order.  BVHAggregate.BVHNodes is private
     /// (Extensions/Aggregate/BVH.fs:9), so the TLAS is rebuilt here with the public, deterministic
     /// BVHNode.Build on a copy of the SAME input: same nodes, same permutation as the CPU aggregate.
-    let withDeviceScene (camera: CameraBase) (lightSampler: LightSamplerBase) (original: PrimitiveInstance array) (device: int)
-                        (body: nativeint -> unit) =
+    let withFlattenedScene (camera: CameraBase) (lightSampler: LightSamplerBase) (original: PrimitiveInstance array)
+                           (body: Native.BnSceneDesc -> unit) =
         if original.Length = 0 then
             failwith "GpuScene: Instances not set (Scene.Render must assign IGpuIntegrator.Instances)"
         let ordered = Array.copy original
@@ -403,12 +423,35 @@ module GpuScene =
         desc.lightCount <- uint32 lightArr.Length
         desc.camera <- cam
 
-        let mutable scene = 0n
-        Native.check (Native.bn_scene_create (&desc, device, &scene)) // copies; keeps no host pointers
+        body desc // every array above stays pinned until `body` returns; the library copies and keeps no host pointers
+
+    /// One device: bn_scene_create / bn_scene_destroy around `body`.
+    let withDeviceScene (camera: CameraBase) (lightSampler: LightSamplerBase) (original: PrimitiveInstance array) (device: int)
+                        (body: nativeint -> unit) =
+        withFlattenedScene camera lightSampler original (fun desc ->
+            let mutable d = desc
+            let mutable scene = 0n
+            Native.check (Native.bn_scene_create (&d, device, &scene))
+            try
+                body scene
+            finally
+                Native.bn_scene_destroy scene)
+
+    /// Several devices: the scene is flattened ONCE (above) and uploaded to every device by bn_multi_scene_create.
+    let withMultiDeviceScene (camera: CameraBase) (lightSampler: LightSamplerBase) (original: PrimitiveInstance array) (devices: int array)
+                             (body: nativeint -> unit) =
+        let pin = GCHandle.Alloc(devices, GCHandleType.Pinned) // (`fixed` is not available inside the closure below)
         try
-            body scene
+            withFlattenedScene camera lightSampler original (fun desc ->
+                let mutable d = desc
+                let mutable scene = 0n
+                Native.check (Native.bn_multi_scene_create (&d, pin.AddrOfPinnedObject(), devices.Length, &scene))
+                try
+                    body scene
+                finally
+                    Native.bn_multi_scene_destroy scene)
         finally
-            Native.bn_scene_destroy scene
+            pin.Free()
 
 /// kind: 0 = PathTracingIntegrator.Li (PathTracing.fs:14-81), 1 = DirectIntegrator.Li (Direct.fs:10-40),
 /// 2 = NormalIntegrator.Li (Normal.fs:10-17) — all under ProgressiveIntegrator.Render (Integrator.fs:22-55).
@@ -417,6 +460,11 @@ type GpuProgressiveIntegrator(spp: int, maxDepth: int, rrDepth: int, kind: int) 
     inherit ProgressiveIntegrator(spp)
     let mutable instances: PrimitiveInstance array = [||]
     member val Device = 0 with get, set
+    /// More than one entry: the frame is rendered by all of them inside ONE bn_render_multi call (e.g. [| 0 .. 7 |] on the
+    /// 8 x B200 box) — the GPU counterpart of Parallel.ForEach over the tiles (Integrator.fs:46-54).
+    member val Devices: int array = [||] with get, set
+    /// 0 auto, 1 sample split, 2 tile split (BN_PARTITION_*)
+    member val Partition = 0 with get, set
     member val LastStats = Native.BnStats() with get, set
     member this.MaxDepth = maxDepth
     member this.RRDepth = rrDepth
@@ -429,27 +477,37 @@ type GpuProgressiveIntegrator(spp: int, maxDepth: int, rrDepth: int, kind: int) 
     override this.Render(camera, film, _aggregate, lightSampler) =
         use pixels = fixed film.Pixels // Vector3[W*H] == float[3*W*H], already Y-flipped (Film.fs:41-46); pinned for the whole call
         let filmRgb = NativePtr.toNativeInt pixels
-        GpuScene.withDeviceScene camera lightSampler instances this.Device (fun scene ->
-            let mutable p = Native.BnRenderParams()
-            p.width <- film.ImageWidth
-            p.height <- film.ImageHeight
-            p.spp <- this.SamplePerPixel
-            p.maxDepth <- maxDepth
-            p.rrDepth <- rrDepth
-            p.frameId <- this.FrameId
-            p.sampleBegin <- 0
-            p.sampleEnd <- this.SamplePerPixel
-            p.x0 <- 0
-            p.y0 <- 0
-            p.x1 <- film.ImageWidth
-            p.y1 <- film.ImageHeight
-            p.flags <- 0u
-            p.interleaveCount <- 1
-            p.interleaveIndex <- 0
-            p.integrator <- kind
-            let mutable stats = Native.BnStats()
-            Native.check (Native.bn_render (scene, &p, filmRgb, &stats))
-            this.LastStats <- stats)
+        let mutable p = Native.BnRenderParams()
+        p.width <- film.ImageWidth
+        p.height <- film.ImageHeight
+        p.spp <- this.SamplePerPixel
+        p.maxDepth <- maxDepth
+        p.rrDepth <- rrDepth
+        p.frameId <- this.FrameId
+        p.sampleBegin <- 0
+        p.sampleEnd <- this.SamplePerPixel
+        p.x0 <- 0
+        p.y0 <- 0
+        p.x1 <- film.ImageWidth
+        p.y1 <- film.ImageHeight
+        p.flags <- 0u
+        p.interleaveCount <- 1
+        p.interleaveIndex <- 0
+        p.integrator <- kind
+        let p0 = p
+        if this.Devices.Length > 1 then
+            GpuScene.withMultiDeviceScene camera lightSampler instances this.Devices (fun scene ->
+                let mutable q = p0
+                let mutable stats = Native.BnStats()
+                Native.check (Native.bn_render_multi (scene, &q, this.Partition, filmRgb, &stats))
+                this.LastStats <- stats)
+        else
+            let device = if this.Devices.Length = 1 then this.Devices[0] else this.Device
+            GpuScene.withDeviceScene camera lightSampler instances device (fun scene ->
+                let mutable q = p0
+                let mutable stats = Native.BnStats()
+                Native.check (Native.bn_render (scene, &q, filmRgb, &stats))
+                this.LastStats <- stats)
         this.FrameId <- this.FrameId + 1 // Integrator.fs:55
 
 /// PSSMLTIntegrator.Render (PSSMLT.fs:379-414) on the device.
@@ -510,6 +568,7 @@ type GpuPSSMLTIntegrator
 // (1) Extensions/Scene/Loader.fs, IntegratorInfo.ToIntegrator (:185-204) — four more arms, placed before
 //     the catch-all; the pssmlt arm reuses the bindings the "pssmlt" arm computes:
 //
+//         (optionally `GpuProgressiveIntegrator(...) |> fun g -> g.Devices <- [| 0 .. Native.bn_device_count () - 1 |]; g` to use every GPU of the box)
 //         | "gpu-path-tracing" -> GpuProgressiveIntegrator(spp, maxDepth, rrDepth, 0)
 //         | "gpu-direct" -> GpuProgressiveIntegrator(spp, maxDepth, rrDepth, 1)
 //         | "gpu-normal" -> GpuProgressiveIntegrator(spp, maxDepth, rrDepth, 2)
