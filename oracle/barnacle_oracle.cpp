@@ -1255,6 +1255,28 @@ BO_API int bo_render(const BoScene* sc, const BnRenderParams* p, float* film, ui
   return 0;
 }
 
+// Film.PostProcess (Film.fs:21-30) + the Rgba32 conversion of Film.Save (Film.fs:55-66): tone 0 identity, 1 aces, 2 gamma.
+// Vector3.Clamp(x, 0, 1) = Min(Max(x, 0), 1) with minps / maxps semantics (NaN in x -> the bound: the NaN speckles of the
+// published renders are black); ImageSharp's Rgba32(Vector3) packs with x * 255 + 0.5, clamped, truncated.
+BO_API int bo_film_to_rgba8(const float* film, int w, int h, int tone, uint8_t* rgba) {
+  if (!film || !rgba || w <= 0 || h <= 0 || tone < 0 || tone > 2) return -1;
+  const float gamma = 1.f / 2.2f;
+  for (int64_t i = 0; i < (int64_t)w * h; ++i) {
+    for (int c = 0; c < 3; ++c) {
+      float x = film[i * 3 + c];
+      if (tone == 1) x = x * (2.51f * x + 0.03f) / (x * (2.43f * x + 0.59f) + 0.14f);
+      else if (tone == 2) x = std::pow(x, gamma);
+      x = x > 0.f ? x : 0.f;   // maxps(x, 0): the second operand when x is NaN
+      x = x < 1.f ? x : 1.f;   // minps(x, 1)
+      float v = x * 255.f + 0.5f;
+      v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);
+      rgba[i * 4 + c] = (uint8_t)v;
+    }
+    rgba[i * 4 + 3] = 255;
+  }
+  return 0;
+}
+
 // CameraBase.GeneratePrimaryRay from explicit samples (tests/test_oracle_pssmlt_chain.py): u = uPixel.xy, uLens.xy.
 BO_API void bo_camera_ray(const BoScene* sc, int width, int height, int x, int y, const float* u, BnRay* out) {
   const Ray r = primary_ray(sc->s.cam, width, height, x, y, V2{u[0], u[1]}, V2{u[2], u[3]});

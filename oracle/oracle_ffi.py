@@ -190,6 +190,16 @@ def mlt_sampler_script(seed_state: int, large_step_prob: float, strategy: int, p
     return out
 
 
+def film_to_rgba8(film: np.ndarray, width: int, height: int, tone: int) -> np.ndarray:
+    """Film.PostProcess + Rgba32 (Base/Film.fs:21-30,55-66): W*H*3 float32 -> [H, W, 4] uint8."""
+    film = np.ascontiguousarray(film, dtype=np.float32)
+    out = np.empty((height, width, 4), dtype=np.uint8)
+    lib = load()
+    lib.bo_film_to_rgba8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    assert lib.bo_film_to_rgba8(film.ctypes.data, width, height, tone, out.ctypes.data) == 0
+    return out
+
+
 def set_portable_math(on: bool) -> None:
     load().bo_set_portable_math(1 if on else 0)
 

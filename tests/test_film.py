@@ -41,6 +41,20 @@ def test_film_to_rgba8_matches_restatement(lib, tone):
         assert got[0, 3, :3].tolist() == [0, 255, 0]               # NaN -> 0, +inf -> 1
 
 
+@pytest.mark.parametrize("tone", ["identity", "aces", "gamma"])
+def test_host_film_to_rgba8_equals_the_oracle_restatement(lib, oracle_lib, tone):
+    """The product's host-side conversion and the oracle's restatement of Film.PostProcess / Rgba32 (oracle/barnacle_oracle.cpp:
+    bo_film_to_rgba8) byte for byte — both call glibc's powf for the gamma curve, as MathF.Pow does on Linux."""
+    from oracle import oracle_ffi
+    rng = np.random.default_rng(7)
+    w, h = 64, 31
+    film = Film(w, h, tone)
+    film.Pixels[:] = np.exp(rng.normal(-1.0, 2.5, size=(h * w, 3))).astype(np.float32)
+    film.Pixels[:6] = [[0, 0, 0], [1, 1, 1], [-0.5, 2.0, 0.25], [np.nan, np.inf, 1e-30], [0.18, 0.5, 0.9], [-np.inf, -0.0, 1e30]]
+    want = oracle_ffi.film_to_rgba8(film.Pixels, w, h, {"identity": 0, "aces": 1, "gamma": 2}[tone])
+    assert np.array_equal(film.to_rgba8(), want)
+
+
 def test_film_to_rgba8_rejects_bad_arguments(lib):
     out = (ctypes.c_uint8 * 16)()
     assert lib.bn_host_film_to_rgba8(None, 2, 2, 0, out) == _ffi.BN_ERR_INVALID

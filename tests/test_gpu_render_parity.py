@@ -111,6 +111,11 @@ def test_film_to_rgba8_device_matches_host():
         _ffi.check(lib.bn_film_to_rgba8_device(g._h, d_film.data_ptr(), W, H, tone, d_out.data_ptr(), None))
         diff = np.abs(d_out.cpu().numpy().astype(int) - host.astype(int))
         assert diff.max() <= (1 if tone == 2 else 0)      # gamma: libdevice vs glibc powf may differ by one 8-bit step
+        # ... and against the ORACLE's restatement of Film.PostProcess + Rgba32 (Film.fs:21-30,55-66), not only the product's own host code
+        from oracle import oracle_ffi
+        want = oracle_ffi.film_to_rgba8(film, W, H, tone)
+        diff = np.abs(d_out.cpu().numpy().astype(int) - want.astype(int))
+        assert diff.max() <= (1 if tone == 2 else 0) and (diff != 0).mean() < 1e-3
 
 
 def test_window_and_sample_range_sharding():
