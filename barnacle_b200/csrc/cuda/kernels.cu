@@ -848,6 +848,22 @@ int bnint::scene_film(BnScene* s, size_t len, float** out) {
   return BN_OK;
 }
 
+// ---- the traversal kernels for other wavefronts (mlt.cu): same queues, same kernels, fix-up launch included ------------
+int bnint::ensure_wave(BnScene* s, size_t cap) { return ensure_wave_buffers(s, cap); }
+
+void bnint::launch_extend(BnScene* s, cudaStream_t stream, const float4* s0, const float4* s1, float4* hits, const int* n_ptr, int* cursor, int* n_defer) {
+  const ExtendIO io{s0, s1, hits, n_ptr, cursor, DeferList{n_defer, s->defer_list}};
+  launch_traverse<false>(s->num_sms * BN_TRAV_GRID_MULT, stream, s->d, io, nullptr);
+  k_traverse_fixup<false, ExtendIO><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
+}
+
+void bnint::launch_shadow(BnScene* s, cudaStream_t stream, const float4* q0, const float4* q1, const float4* q2, const float4* q3, float4* rad, const int* n_ptr,
+                          int* cursor, int* n_defer) {
+  const ShadowIO io{q0, q1, q2, q3, rad, n_ptr, cursor, DeferList{n_defer, s->defer_list}};
+  launch_traverse<true>(s->num_sms * BN_TRAV_GRID_MULT, stream, s->d, io, nullptr);
+  k_traverse_fixup<true, ShadowIO><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
+}
+
 int bnint::render_on_stream(BnScene* s, const BnRenderParams* p, float* d_film, cudaStream_t stream, BnStats* stats) {
   int rc = validate_params(p);
   if (rc != BN_OK) return rc;
@@ -901,7 +917,7 @@ void bn_scene_destroy(BnScene* s) {
   if (s->trace_ctr) cudaFree(s->trace_ctr);
   if (s->trace_dlist) cudaFree(s->trace_dlist);
   release_wave_buffers(s);  // parks the wave, counter and film buffers for the next scene on this device
-  for (void* p : {(void*)s->mlt_f, (void*)s->mlt_i, (void*)s->mlt_w, (void*)s->mlt_cnt, (void*)s->mlt_acc})
+  for (void* p : {(void*)s->mlt_f, (void*)s->mlt_i, (void*)s->mlt_w, (void*)s->mlt_cnt, (void*)s->mlt_acc, (void*)s->mlt_wave_i, (void*)s->mlt_wave_f, (void*)s->mlt_counters})
     if (p) cudaFree(p);
   if (s->mlt_w_host) cudaFreeHost(s->mlt_w_host);
   delete s;

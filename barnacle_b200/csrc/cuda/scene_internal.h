@@ -37,6 +37,11 @@ struct BnScene {
   unsigned long long* mlt_cnt = nullptr;  // 4 counters
   unsigned int* mlt_acc = nullptr;
   size_t mlt_acc_len = 0;
+  int* mlt_wave_i = nullptr;     // wavefront PSSMLT: per-lane sampler + chain state (12 ints / 8 floats per lane)
+  float* mlt_wave_f = nullptr;
+  size_t mlt_wave_len = 0;
+  int* mlt_counters = nullptr;   // ... and the round's queue counters
+  size_t mlt_counters_len = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // frame / batch timing (created once, destroyed with the scene)
   int* trace_ctr = nullptr;      // bn_trace_device scratch: per-chunk cursor + deferred count
   size_t trace_ctr_len = 0;
@@ -54,5 +59,12 @@ namespace bnint {
 int convert_for_device(const BnSceneDesc* desc, bnconv::ConvertedScene& cs);                    // host: flatten + validate
 int scene_from_converted(const bnconv::ConvertedScene& cs, int device, BnScene** out);           // device: one allocation, one copy
 int scene_film(BnScene* s, size_t len, float** out);                                             // the scene's device film, grown on demand
+// the wavefront's traversal stages for other integrators (mlt.cu): closest hit for the rays (s0, s1) -> hits; any hit for the
+// shadow queue (q0..q3) + connect into rad; both with their exact fix-up launch.  Counters: *n_ptr rays, a work cursor and a
+// deferred count (zeroed by the caller).  ensure_wave grows the scene's queues to `cap` paths.
+int ensure_wave(BnScene* s, size_t cap);
+void launch_extend(BnScene* s, cudaStream_t stream, const float4* s0, const float4* s1, float4* hits, const int* n_ptr, int* cursor, int* n_defer);
+void launch_shadow(BnScene* s, cudaStream_t stream, const float4* q0, const float4* q1, const float4* q2, const float4* q3, float4* rad, const int* n_ptr,
+                   int* cursor, int* n_defer);
 int render_on_stream(BnScene* s, const BnRenderParams* p, float* d_film, cudaStream_t stream, BnStats* stats);  // film stays on the device
 }  // namespace bnint

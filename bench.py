@@ -246,6 +246,18 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
     e2e_s = time.perf_counter() - t0
     # stopped only now (an exiting NVML client can stall the next CUDA calls); its report covers t_wall0..t_wall1, the timed region
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    # the same 10.5 M mutations over four times the chains (N = 1 only; outside the timed regions): from ~10^5 chains up the device
+    # integrator runs the chains as a wavefront through the path tracer's traversal kernels instead of one chain per thread
+    more = None
+    if world == 1 and rank == 0 and not args.no_configs:
+        big = make_mlt_params(W, H, SPP, i.max_depth, i.rr_depth, 0, i.n_bootstrap, 4 * i.n_chains, "Gaussian", i.large_step_prob)
+        film.zero_()
+        render_pssmlt_sharded(gpu, big, film, None, stream)
+        ev0.record(); stb = render_pssmlt_sharded(gpu, big, film, None, stream); ev1.record(); torch.cuda.synchronize()
+        mb = ev0.elapsed_time(ev1)
+        more = {"n_chains": 4 * i.n_chains, "value": stb.rays / mb / 1e3, "unit": "Mrays/s", "ms_per_step": mb, "mutations_per_s": stb.proposed / (mb * 1e-3),
+                "acceptance_rate": stb.accepted / max(stb.proposed, 1), "bootstrap_ms": stb.bootstrap_ms, "chains_ms": stb.chains_ms,
+                "form": "bootstrap and chains as waves through the wavefront's traversal kernels (CUDA-graph replay per mutation round)"}
     agg = torch.tensor([ms, float(rays), float(muts), float(acc), e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = agg.clone()
@@ -261,7 +273,7 @@ def run_pssmlt(args, scene_file, W, H, SPP, label):
                        "l2_flush": "film (12.6 MB) rewritten each step; working set (primary samples + scene) is L2-resident by design"},
             "mutations_per_s": muts / (ms * 1e-3), "acceptance_rate": acc / max(muts, 1.0), "gpu_launches": 2 * args.steps * world,
             "e2e": {"value": rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12, "ms_per_step": e2e_s / args.steps * 1e3},
-            "clocks": clk,
+            "clocks": clk, "more_chains": more,
             "roofline": {"bound": "hbm", "kernel": "k_mlt_chains (one Markov chain per thread)", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
                          "note": "per-thread megakernel on the exact per-lane traversal (divergence- and latency-bound, scene in L2); no bytes-per-mutation roofline is claimed for this row"},
             "cpu_baseline": None}))

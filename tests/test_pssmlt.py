@@ -52,9 +52,14 @@ def test_oracle_pssmlt_chain_split_is_additive(lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("form", ["BN_MLT_WAVEFRONT", "BN_MLT_MEGAKERNEL"])
 @pytest.mark.parametrize("strategy", ["Gaussian", "Kelemen"])
 @pytest.mark.parametrize("name", ["cbox_pt", "cbox_bunny"])
-def test_gpu_pssmlt_matches_oracle(name, strategy):
+def test_gpu_pssmlt_matches_oracle(name, strategy, form, monkeypatch):
+    """Both forms of the device integrator — a wavefront over chains through the path tracer's traversal kernels (what large
+    chain counts and the bootstrap run) and one chain per thread (what small chain counts run) — evolve every chain as the
+    oracle does: same bootstrap weights, B, accepted count per chain, ray count."""
+    monkeypatch.setenv(form, "1")
     set_portable_math(True)
     scene = load_scene(name)
     g, o = scene.gpu(), OracleScene(scene.desc)
@@ -80,7 +85,9 @@ def test_gpu_pssmlt_matches_oracle(name, strategy):
 
 
 @pytest.mark.gpu
-def test_gpu_pssmlt_chain_shards_add_up():
+@pytest.mark.parametrize("form", ["BN_MLT_WAVEFRONT", "BN_MLT_MEGAKERNEL"])
+def test_gpu_pssmlt_chain_shards_add_up(form, monkeypatch):
+    monkeypatch.setenv(form, "1")
     set_portable_math(True)
     scene = load_scene("cbox_pt")
     g = scene.gpu()
