@@ -110,9 +110,10 @@ int bn_multi_scene_create(const BnSceneDesc* desc, const int32_t* devices, int32
   if (ndev <= 0) { bnhost::set_error("no CUDA device available (the hot path has no CPU fallback)"); return BN_ERR_NO_DEVICE; }
   for (int k = 0; k < n_devices; ++k)
     if (devices[k] < 0 || devices[k] >= ndev) { bnhost::set_error("bn_multi_scene_create: device ordinal out of range"); return BN_ERR_INVALID; }
-  bnconv::ConvertedScene cs;  // flattened ONCE, shared by every upload
-  int rc = bnint::convert_for_device(desc, cs);
+  std::shared_ptr<const bnint::Staged> staged;  // flattened ONCE (or taken from the cache), shared by every upload
+  int rc = bnint::stage_scene(desc, staged);
   if (rc != BN_OK) return rc;
+  const BnCamera camera = desc->camera;
   auto* m = new BnMultiScene();
   m->devices.assign(devices, devices + n_devices);
   m->scenes.assign(n_devices, nullptr);
@@ -122,7 +123,7 @@ int bn_multi_scene_create(const BnSceneDesc* desc, const int32_t* devices, int32
   std::vector<int> rcs(n_devices, BN_OK);
   std::vector<std::string> errs(n_devices);
   auto upload = [&](int k) {
-    rcs[k] = bnint::scene_from_converted(cs, m->devices[k], &m->scenes[k]);
+    rcs[k] = bnint::scene_from_staged(*staged, camera, m->devices[k], &m->scenes[k]);
     if (rcs[k] == BN_OK && cudaStreamCreateWithFlags(&m->streams[k], cudaStreamNonBlocking) != cudaSuccess) rcs[k] = BN_ERR_CUDA;
     if (rcs[k] != BN_OK) errs[k] = bn_last_error();
   };

@@ -442,18 +442,21 @@ bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err) 
   out.lights.resize(d.light_count);
   for (uint32_t i = 0; i < d.light_count; ++i) out.lights[i] = {d.lights[i].emission[0], d.lights[i].emission[1], d.lights[i].emission[2], d.lights[i].two_sided ? 1u : 0u};
   // camera
-  const BnCamera& c = d.camera;
-  if (c.type > BN_CAM_THIN_LENS) { err = "unknown camera type"; return false; }
-  out.cam.type = c.type;
-  out.cam.viewport_h = 2.f * tanf(c.fov_y * 3.14159274101257324f / 360.f);  // Pinhole.fs:15
-  out.cam.aspect = c.aspect_ratio;
-  out.cam.aperture = c.aperture;
-  out.cam.focus = c.focus_distance;
-  out.cam.push_forward = c.push_forward;
+  if (d.camera.type > BN_CAM_THIN_LENS) { err = "unknown camera type"; return false; }
+  convert_camera(d.camera, out.cam);
+  return true;
+}
+
+void convert_camera(const BnCamera& c, bn::GCamera& cam) {
+  cam.type = c.type;
+  cam.viewport_h = 2.f * tanf(c.fov_y * 3.14159274101257324f / 360.f);  // Pinhole.fs:15
+  cam.aspect = c.aspect_ratio;
+  cam.aperture = c.aperture;
+  cam.focus = c.focus_distance;
+  cam.push_forward = c.push_forward;
   bn::GMat43 cm;
   mat43(c.camera_to_world, cm);
-  std::memcpy(out.cam.c2w, cm.m, sizeof cm.m);
-  return true;
+  std::memcpy(cam.c2w, cm.m, sizeof cm.m);
 }
 
 // A/B switch (BN_BINARY_NODES): drop the 4-wide nodes and point everything that names a BLAS root back at the binary tree.

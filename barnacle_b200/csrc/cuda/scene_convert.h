@@ -37,5 +37,6 @@ struct ConvertedScene {
 // sizes and depths the traversal stack can hold) and fills `out`.
 bool convert_scene(const BnSceneDesc& d, ConvertedScene& out, std::string& err);
 void use_binary_nodes(ConvertedScene& cs);
+void convert_camera(const BnCamera& c, bn::GCamera& cam);  // the camera is applied per device scene (it is not part of the cached layout)
 
 }  // namespace bnconv

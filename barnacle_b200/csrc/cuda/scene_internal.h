@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <memory>
 #include <vector>
 
 #include "device_scene.h"
@@ -56,8 +57,9 @@ struct BnScene {
 #include "../../../include/barnacle_b200.h"
 #include "scene_convert.h"
 namespace bnint {
-int convert_for_device(const BnSceneDesc* desc, bnconv::ConvertedScene& cs);                    // host: flatten + validate
-int scene_from_converted(const bnconv::ConvertedScene& cs, int device, BnScene** out);           // device: one allocation, one copy
+struct Staged;                                                                                   // the flattened scene as one host image (kernels.cu)
+int stage_scene(const BnSceneDesc* desc, std::shared_ptr<const Staged>& out);                   // host: flatten + validate (or the cached image)
+int scene_from_staged(const Staged& st, const BnCamera& camera, int device, BnScene** out);     // device: one allocation, one copy
 int scene_film(BnScene* s, size_t len, float** out);                                             // the scene's device film, grown on demand
 // the wavefront's traversal stages for other integrators (mlt.cu): closest hit for the rays (s0, s1) -> hits; any hit for the
 // shadow queue (q0..q3) + connect into rad; both with their exact fix-up launch.  Counters: *n_ptr rays, a work cursor and a
