@@ -1031,12 +1031,11 @@ int bn_render_radiance(BnScene* s, const BnRenderParams* p, float* radiance) {
   BN_CUDA(cudaSetDevice(s->device));
   const size_t len = (size_t)(p->x1 - p->x0) * (p->y1 - p->y0) * (p->sample_end - p->sample_begin) * 3;
   if (len == 0) return BN_OK;
-  float* d = nullptr;
-  BN_CUDA(cudaMalloc((void**)&d, len * sizeof(float)));
+  float* d = nullptr;  // the scene's own film buffer doubles as the export buffer (grown on demand, parked with the scene's buffers)
+  if ((rc = bnint::scene_film(s, len, &d)) != BN_OK) return rc;
   BN_CUDA(cudaMemset(d, 0, len * sizeof(float)));
   rc = render_waves(s, p, nullptr, d, nullptr, nullptr);
   if (rc == BN_OK && !cuda_ok(cudaMemcpy(radiance, d, len * sizeof(float), cudaMemcpyDeviceToHost), "copy radiance")) rc = BN_ERR_CUDA;
-  cudaFree(d);
   return rc;
 }
 

@@ -940,8 +940,8 @@ int bn_render_pssmlt(BnScene* s, const BnMltParams* p, float* film, BnMltStats* 
   return rc;
 }
 
-// test hook (not in the public header): per-chain accepted mutation counts next to the film
-__attribute__((visibility("default"))) int bn_debug_render_pssmlt_chains(BnScene* s, const BnMltParams* p, float* film, BnMltStats* stats, unsigned int* per_chain_accepted) {
+// parity-test entry (declared in the header): per-chain accepted mutation counts next to the film
+int bn_debug_render_pssmlt_chains(BnScene* s, const BnMltParams* p, float* film, BnMltStats* stats, unsigned int* per_chain_accepted) {
   if (!film || !per_chain_accepted) return BN_ERR_INVALID;
   int rc = validate(s, p);
   if (rc != BN_OK) return rc;

@@ -326,6 +326,9 @@ BN_API int bn_render_pssmlt(BnScene* scene, const BnMltParams* params, float* fi
 BN_API int bn_render_pssmlt_device(BnScene* scene, const BnMltParams* params, void* d_film_rgb, void* cuda_stream, BnMltStats* stats);
 /* Phase 1 only: BootstrapWeights[n_bootstrap] (PSSMLT.fs:247-273), HOST pointer — parity tests. */
 BN_API int bn_pssmlt_bootstrap(BnScene* scene, const BnMltParams* params, float* weights);
+/* Parity-test entry: bn_render_pssmlt that also returns the accepted-mutation count of every chain it ran
+ * (per_chain_accepted[chain_end - chain_begin], HOST pointer) — what PSSMLT.fs:412 sums into AcceptedMutationCount. */
+BN_API int bn_debug_render_pssmlt_chains(BnScene* scene, const BnMltParams* params, float* film_rgb, BnMltStats* stats, unsigned int* per_chain_accepted);
 
 /* ---- host-side scene builder (stands in for the managed host: JSON schema of
  *      Extensions/Scene/Loader.fs, Scene.Traverse, BVHNode.Build, AliasTable) -- */
