@@ -137,6 +137,9 @@ struct GCamera {
   float c2w[12];
 };
 
+// Grid of the path re-ordering between bounces (ray_sort.cuh): cell = clamp(int((p - lo) * scale), 0, 2^m - 1) per axis
+struct SortGrid { float lo[3]; float scale[3]; };
+
 struct DScene {
   const GNode* nodes;        // TLAS nodes first, then every mesh's nodes
   GTree tlas;
@@ -158,6 +161,7 @@ struct DScene {
   uint32_t tlas_wroot;         // TLAS root ref in `wide`
   uint32_t pad_wide;
   GCamera cam;
+  SortGrid sort_grid;
 };
 
 }  // namespace bn

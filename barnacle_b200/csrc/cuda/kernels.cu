@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,6 +29,7 @@
 #include "../../../include/barnacle_b200.h"
 #include "device_scene.h"
 #include "scene_convert.h"
+#include "ray_sort.cuh"
 #include "shade.cuh"
 #include "traverse.cuh"
 #include "vecmath.cuh"
@@ -53,6 +55,12 @@ constexpr int kBlock = 128;
                                // (profiles/r02_ab_session1.log): 26 instead of 42 launches per wave, but the drain's code costs the hot loop
                                // three spilled registers — C1 -0.6 %, C2 -0.7 %, C3 -1.9 %, C4 -2.4 % — while the fix-up launches themselves
                                // cost nothing measurable (same build with BN_SEPARATE_FIXUP: +0.1 %).  Off.
+#endif
+#ifndef BN_CAND_PREPASS
+#define BN_CAND_PREPASS 0      // 1: small-TLAS scenes get their candidate masks from a full-width pre-pass kernel (k_candidates) before each
+                               // traversal launch instead of from the refilled lanes of the persistent loop.  Measured on the B200
+                               // (profiles/r02_ab_session12_*.log) and OFF: C1 -11.7 %, C2 -5.3 %: the pass is cheap where it is (other warps
+                               // hide its latency) and the pre-pass adds a kernel that runs at 40 % of the issue rate
 #endif
 #ifndef BN_TRAV_GRID_MULT
 #define BN_TRAV_GRID_MULT 9    // persistent grid = SMs x this
@@ -147,18 +155,46 @@ struct ExtendIO {
   const int* __restrict__ n_ptr;
   int* cur;
   DeferList deferred;
+  const uint32_t* __restrict__ cand_words;  // k_candidates' output (small-TLAS scenes)
+  // ray_sort.cuh: slot i of the ordered queue is path perm[i] of the state planes (nullptr: i itself).  The refill that
+  // claims slot i gathers the two planes it needs anyway (origin, direction) and leaves them at slot i of the planes t0, t1,
+  // so that shade reads them coalesced (two coalesced stores per ray here); shade fetches the third plane through perm.
+  const uint32_t* __restrict__ perm;
+  float4* __restrict__ t0;
+  float4* __restrict__ t1;
+  static constexpr bool kHasCand = BN_CAND_PREPASS != 0;
+  BN_DEV uint32_t cand(int i) const { return cand_words[i]; }
   BN_DEV int count() const { return *n_ptr; }
   BN_DEV int* cursor() const { return cur; }
   BN_DEV void load(int i, float3& o, float3& d, float& t) const {
-    const float4 a = s0[i], b = s1[i];
-    o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
+    if (perm) {
+      const int src = (int)perm[i];
+      const float4 a = s0[src], b = s1[src];
+      t0[i] = a; t1[i] = b;
+      o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
+    } else {
+      const float4 a = s0[i], b = s1[i];
+      o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
+    }
     t = CUDART_INF_F;  // PathTracing.fs:25
   }
+  BN_DEV void load_ray(int i, float3& o, float3& d, float& t) const { load(i, o, d, t); }
   BN_DEV void store(int i, const TraceResult& r) const {
     hits[i] = make_float4(r.t, __int_as_float(r.inst), __int_as_float(r.prim), 0.f);
   }
   BN_DEV void defer(int i) const { deferred.push(i); }
-  BN_DEV void prefetch(int i) const { prefetch_l2(s0 + i); prefetch_l2(s1 + i); }
+  BN_DEV void prefetch(int i) const {
+    if (perm) {
+      // two stages: the perm line one more window ahead (32 entries per 128-B line), and through the entry that an earlier
+      // refill prefetched, the state it points at
+      if ((i & 31) == 0 && i + kPrefetchAhead < *n_ptr) prefetch_l2(perm + i + kPrefetchAhead);
+      const int src = (int)perm[i];
+      prefetch_l2(s0 + src); prefetch_l2(s1 + src);
+    } else {
+      prefetch_l2(s0 + i); prefetch_l2(s1 + i);
+    }
+    if (kHasCand && (i & 31) == 0) prefetch_l2(cand_words + i);  // 32 words per 128-B line
+  }
 };
 // The deferred rays (zero / denormal direction component: normally none, a handful at most) re-traced with the exact form.
 // Out of line on purpose: the hot loop's register allocation must not see this code.
@@ -201,9 +237,27 @@ __global__ void __launch_bounds__(kBlock) k_traverse_fixup(DScene sc, IO io) {
   traverse_deferred<ANY>(sc, io, io.deferred.list, *io.deferred.count);
 }
 
+// Small-TLAS scenes: the candidate word of every queued ray (traverse.cuh: candidate_word — the fast-form check and the pass
+// over the <= 16 octant-ordered instance boxes with the ray's initial t), one thread per ray with all 32 lanes of a warp
+// busy.  In the persistent loop this pass ran on the 14-20 lanes a refill fills and was 16 % of the extend kernel's
+// instructions on C2; here it streams (32 B in, 4 B out per ray).  Same device function, same bits.
+template <class IO>
+__global__ void __launch_bounds__(256) k_candidates(const __grid_constant__ DScene sc, const __grid_constant__ IO io, uint32_t* __restrict__ cand) {
+  const int n = io.count();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float3 o, d;
+    float t;
+    io.load_ray(i, o, d, t);
+    cand[i] = candidate_word(sc, o, d, t);
+  }
+}
+
 // host side: the 4-wide-node kernel when the scene has such nodes (sc.wide), else the binary-node kernel
 template <bool ANY, class IO>
 void launch_traverse(int grid, cudaStream_t stream, const DScene& sc, const IO& io, int* done) {
+  if constexpr (io_has_cand<IO>::value) {
+    if (sc.flat_tlas != nullptr) k_candidates<IO><<<grid, 256, 0, stream>>>(sc, io, const_cast<uint32_t*>(io.cand_words));
+  }
   if (sc.wide != nullptr) k_traverse<ANY, true, IO><<<grid, kBlock, 0, stream>>>(sc, io, done);
   else k_traverse<ANY, false, IO><<<grid, kBlock, 0, stream>>>(sc, io, done);
 }
@@ -213,7 +267,7 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
                                                   const float4* __restrict__ s2, const float4* __restrict__ hits, float4* __restrict__ o0,
                                                   float4* __restrict__ o1, float4* __restrict__ o2, float4* __restrict__ q0, float4* __restrict__ q1,
                                                   float4* __restrict__ q2, float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr,
-                                                  int* n_out, int* n_shadow, int* cursor, unsigned long long* shadow_ref) {
+                                                  int* n_out, int* n_shadow, int* cursor, unsigned long long* shadow_ref, uint16_t* __restrict__ key_out, const uint32_t* __restrict__ perm) {
   const int n = *n_ptr;
   unsigned ref_total = 0;  // lane 0: reference-equivalent shadow rays of this warp's chunks
   int next = warp_fetch(cursor);
@@ -223,7 +277,7 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
     next = warp_fetch(cursor);  // claimed one chunk ahead: the atomic's round trip overlaps this chunk's shading
     if (next + lane_id() < n) {  // ... and so does the DRAM latency of its inputs
       const int j = next + lane_id();
-      prefetch_l2(s0 + j); prefetch_l2(s1 + j); prefetch_l2(s2 + j); prefetch_l2(hits + j);
+      prefetch_l2(s0 + j); prefetch_l2(s1 + j); prefetch_l2(s2 + (perm ? (int)perm[j] : j)); prefetch_l2(hits + j);
     }
     const int i = base + lane_id();
     bool alive = false, has_shadow = false, ref_shadow = false;
@@ -234,7 +288,7 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
     float3 sh_wi = splat(0.f), sh_a = splat(0.f), sh_b = splat(0.f);
     float sh_tmax = 0.f;
     if (i < n) {
-      const float4 a = s0[i], b = s1[i], c = s2[i], h = hits[i];
+      const float4 a = s0[i], b = s1[i], c = s2[perm ? (int)perm[i] : i], h = hits[i];  // third plane: where the previous shade left it (ray_sort.cuh)
       shade_lane(sc, wp.integrator, wp.rr_depth, wp.max_depth, wp.flags, bounce, a, b, c, h, rad, alive, has_shadow, ref_shadow, P, nd, beta, bs_pdf, rng, pid,
                  sh_wi, sh_a, sh_b, sh_tmax);
     }
@@ -243,6 +297,7 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
       o0[pos] = make_float4(P.x, P.y, P.z, nd.x);
       o1[pos] = make_float4(nd.y, nd.z, beta.x, beta.y);
       o2[pos] = make_float4(beta.z, bs_pdf, __uint_as_float(rng), __int_as_float(pid));
+      if (key_out) key_out[pos] = (uint16_t)sort_key(sc.sort_grid, P, nd);  // for the re-ordering before the next extend (ray_sort.cuh)
     }
     const int spos = warp_append(n_shadow, has_shadow);
     if (has_shadow) {
@@ -266,8 +321,16 @@ struct ShadowIO {
   const int* __restrict__ n_ptr;
   int* cur;
   DeferList deferred;
+  const uint32_t* __restrict__ cand_words;  // k_candidates' output (small-TLAS scenes)
+  static constexpr bool kHasCand = BN_CAND_PREPASS != 0;
+  BN_DEV uint32_t cand(int i) const { return cand_words[i]; }
   BN_DEV int count() const { return *n_ptr; }
   BN_DEV int* cursor() const { return cur; }
+  BN_DEV void load_ray(int i, float3& o, float3& d, float& t) const {
+    const float4 a = q0[i], b = q1[i];
+    o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
+    t = b.z;
+  }
   BN_DEV void load(int i, float3& o, float3& d, float& t) const {
     const float4 a = q0[i], b = q1[i];
     o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
@@ -275,7 +338,10 @@ struct ShadowIO {
     // what store() reads if the ray turns out unoccluded: in L2 by the time the traversal is done
     prefetch_l2(q2 + i); prefetch_l2(q3 + i); prefetch_l2(rad + __float_as_int(b.w));
   }
-  BN_DEV void prefetch(int i) const { prefetch_l2(q0 + i); prefetch_l2(q1 + i); }
+  BN_DEV void prefetch(int i) const {
+    prefetch_l2(q0 + i); prefetch_l2(q1 + i);
+    if (kHasCand && (i & 31) == 0) prefetch_l2(cand_words + i);
+  }
   BN_DEV void store(int i, const TraceResult& r) const {
     if (r.hit) return;  // occluded
     const float4 b = q1[i], c = q2[i], e = q3[i];
@@ -414,11 +480,15 @@ namespace {
 struct WaveBuffers {
   int device = -1;
   size_t cap = 0;
-  float4* state[2] = {nullptr, nullptr};
+  float4* state[3] = {nullptr, nullptr, nullptr};
+  uint32_t* sort_perm = nullptr;
+  uint16_t* sort_key = nullptr;
+  uint32_t* sort_bins = nullptr;
   float4* hits = nullptr;
   float4* shq = nullptr;
   float4* rad = nullptr;
   int* defer_list = nullptr;
+  uint32_t* cand = nullptr;
   // the small per-render buffers travel with the bundle so that creating / destroying a scene
   // (the e2e path does both per frame) allocates nothing once a device is warm
   int* counters = nullptr;
@@ -524,7 +594,7 @@ size_t wave_capacity_paths() {
 }
 
 void free_wave_buffers(WaveBuffers& w) {
-  for (void* p : {(void*)w.state[0], (void*)w.state[1], (void*)w.hits, (void*)w.shq, (void*)w.rad, (void*)w.defer_list, (void*)w.counters, (void*)w.shadow_ref, (void*)w.film, w.arena})
+  for (void* p : {(void*)w.state[0], (void*)w.state[1], (void*)w.state[2], (void*)w.sort_perm, (void*)w.sort_key, (void*)w.sort_bins, (void*)w.hits, (void*)w.shq, (void*)w.rad, (void*)w.defer_list, (void*)w.cand, (void*)w.counters, (void*)w.shadow_ref, (void*)w.film, w.arena})
     if (p) cudaFree(p);
   w = WaveBuffers();
 }
@@ -534,12 +604,12 @@ void release_wave_buffers(BnScene* s) {  // park the scene's buffers for the nex
   WaveBuffers w;
   const bool park = std::getenv("BN_NO_BUFFER_CACHE") == nullptr;  // a host that shares the GPU can opt out of the retained footprint
   w.device = s->device; w.cap = s->cap;
-  w.state[0] = s->state[0]; w.state[1] = s->state[1]; w.hits = s->hits; w.shq = s->shq; w.rad = s->rad; w.defer_list = s->defer_list;
+  w.state[0] = s->state[0]; w.state[1] = s->state[1]; w.state[2] = s->state[2]; w.sort_perm = s->sort_perm; w.sort_key = s->sort_key; w.sort_bins = s->sort_bins; w.hits = s->hits; w.shq = s->shq; w.rad = s->rad; w.defer_list = s->defer_list; w.cand = s->cand;
   w.counters = s->counters; w.counters_len = s->counters_len; w.shadow_ref = s->shadow_ref; w.film = s->film; w.film_len = s->film_len;
   w.arena = s->arena; w.arena_bytes = s->arena_bytes;
   s->arena = nullptr; s->arena_bytes = 0;
   s->cap = 0;
-  s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
+  s->state[0] = s->state[1] = s->state[2] = nullptr; s->sort_perm = nullptr; s->sort_key = nullptr; s->sort_bins = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr; s->cand = nullptr;
   s->counters = nullptr; s->counters_len = 0; s->shadow_ref = nullptr; s->film = nullptr; s->film_len = 0;
   if (!park) { free_wave_buffers(w); return; }
   std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -561,7 +631,7 @@ void adopt_parked_buffers(BnScene* s) {
       const WaveBuffers w = g_pool[k];
       g_pool.erase(g_pool.begin() + (long)k);
       s->cap = w.cap;
-      s->state[0] = w.state[0]; s->state[1] = w.state[1]; s->hits = w.hits; s->shq = w.shq; s->rad = w.rad; s->defer_list = w.defer_list;
+      s->state[0] = w.state[0]; s->state[1] = w.state[1]; s->state[2] = w.state[2]; s->sort_perm = w.sort_perm; s->sort_key = w.sort_key; s->sort_bins = w.sort_bins; s->hits = w.hits; s->shq = w.shq; s->rad = w.rad; s->defer_list = w.defer_list; s->cand = w.cand;
       s->counters = w.counters; s->counters_len = w.counters_len; s->shadow_ref = w.shadow_ref; s->film = w.film; s->film_len = w.film_len;
       s->arena = w.arena; s->arena_bytes = w.arena_bytes;
       return;
@@ -573,15 +643,17 @@ constexpr int BN_ERR_NOMEM_RETRY = -100;  // internal: cudaErrorMemoryAllocation
 int ensure_wave_buffers(BnScene* s, size_t cap) {
   if (s->cap >= cap) return BN_OK;
   auto drop = [&]() {
-    for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list})
+    for (void* p : {(void*)s->state[0], (void*)s->state[1], (void*)s->state[2], (void*)s->sort_perm, (void*)s->sort_key, (void*)s->sort_bins, (void*)s->hits, (void*)s->shq, (void*)s->rad, (void*)s->defer_list, (void*)s->cand})
       if (p) cudaFree(p);
     s->cap = 0;
-    s->state[0] = s->state[1] = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr;
+    s->state[0] = s->state[1] = s->state[2] = nullptr; s->sort_perm = nullptr; s->sort_key = nullptr; s->sort_bins = nullptr; s->hits = s->shq = s->rad = nullptr; s->defer_list = nullptr; s->cand = nullptr;
   };
   drop();
   const struct { void** p; size_t bytes; } want[] = {
-      {(void**)&s->state[0], cap * 3 * sizeof(float4)}, {(void**)&s->state[1], cap * 3 * sizeof(float4)}, {(void**)&s->hits, cap * sizeof(float4)},
-      {(void**)&s->shq, cap * 4 * sizeof(float4)},      {(void**)&s->rad, cap * sizeof(float4)},          {(void**)&s->defer_list, cap * sizeof(int)}};
+      {(void**)&s->state[0], cap * 3 * sizeof(float4)}, {(void**)&s->state[1], cap * 3 * sizeof(float4)}, {(void**)&s->state[2], cap * 2 * sizeof(float4)}, {(void**)&s->sort_perm, cap * sizeof(uint32_t)},
+      {(void**)&s->sort_key, cap * sizeof(uint16_t)}, {(void**)&s->sort_bins, 2 * kSortBins * sizeof(uint32_t)}, {(void**)&s->hits, cap * sizeof(float4)},
+      {(void**)&s->shq, cap * 4 * sizeof(float4)},      {(void**)&s->rad, cap * sizeof(float4)},          {(void**)&s->defer_list, cap * sizeof(int)},
+      {(void**)&s->cand, BN_CAND_PREPASS ? cap * sizeof(uint32_t) : (size_t)16}};
   for (const auto& w : want) {
     const cudaError_t e = cudaMalloc(w.p, w.bytes);
     if (e == cudaErrorMemoryAllocation) {
@@ -592,6 +664,7 @@ int ensure_wave_buffers(BnScene* s, size_t cap) {
     }
     if (!cuda_ok(e, "cudaMalloc(wave buffers)")) { drop(); return BN_ERR_CUDA; }
   }
+  if (!cuda_ok(cudaMemset(s->sort_bins, 0, 2 * kSortBins * sizeof(uint32_t)), "cudaMemset(sort bins)")) { drop(); return BN_ERR_CUDA; }
   s->cap = cap;
   return BN_OK;
 }
@@ -667,6 +740,9 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
     const int tgrid = s->num_sms * BN_TRAV_GRID_MULT;
     DScene dsc = s->d;
     if (p->flags & BN_RENDER_FORCE_EXACT) dsc.all_finite = 0u;  // every ray is deferred to the exact fix-up kernel
+    // paths ordered before every extend launch but the first (ray_sort.cuh); BN_SORT=0 switches it off (A/B, parity tests)
+    const bool order_paths = !(std::getenv("BN_SORT") && std::atoi(std::getenv("BN_SORT")) == 0);
+    const int order_from = std::getenv("BN_SORT_FROM") ? std::max(1, std::atoi(std::getenv("BN_SORT_FROM"))) : 1;  // first ordered bounce (primary rays are coherent as generated)
     const bool separate_fixup = !BN_INKERNEL_DRAIN || (p->flags & BN_RENDER_FORCE_EXACT) != 0 || std::getenv("BN_SEPARATE_FIXUP") != nullptr;
     // BN_RENDER_PROFILE: bracket every launch with events on the launching stream
     const bool profile = (p->flags & BN_RENDER_PROFILE) != 0 && stats != nullptr;
@@ -716,25 +792,40 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         k_raygen<<<grid, kBlock, 0, stream>>>(s->d, wp, A, A + cp, A + 2 * cp, s->rad, n_active);
         prof_end();
         ++launches;
+        float4* const T = s->state[2];  // the bounce's paths in its ordering (written by extend's refills, read by shade)
         for (int b = 0; b < D; ++b) {
+          const uint32_t* perm = nullptr;
+          if (order_paths && b >= order_from) {
+            // the paths that survived bounce b-1, ranked by (direction octant, origin cell): ray_sort.cuh
+            prof_begin(3);
+            k_sort_hist<<<s->num_sms * 4, kSortThreads, 0, stream>>>(s->sort_key, n_active + b * CS, s->sort_bins);
+            k_sort_scan<<<1, kSortScanThreads, 0, stream>>>(s->sort_bins, s->sort_bins + kSortBins);
+            k_sort_rank<<<s->num_sms * 4, kSortThreads, 0, stream>>>(s->sort_key, n_active + b * CS, s->sort_bins + kSortBins, s->sort_perm);
+            prof_end();
+            launches += 3;
+            perm = s->sort_perm;
+          }
+          // ordered bounce: extend reads planes 0, 1 of A through perm and leaves them in order in T, where shade reads them;
+          // plane 2 stays in A and shade reads it through perm
+          const float4* const S = perm ? T : A;
           prof_begin(0);
-          const ExtendIO eio{A, A + cp, s->hits, n_active + b * CS, cursors + (3 * b) * CS, DeferList{n_defer + (2 * b) * CS, s->defer_list}};
+          const ExtendIO eio{A, A + cp, s->hits, n_active + b * CS, cursors + (3 * b) * CS, DeferList{n_defer + (2 * b) * CS, s->defer_list}, s->cand, perm, T, T + cp};
           // the last CTA to finish drains the deferred rays; with BN_RENDER_FORCE_EXACT every ray is deferred and a
           // full-width fix-up launch does the work instead
           launch_traverse<false>(tgrid, stream, dsc, eio, separate_fixup ? nullptr : n_done + (2 * b) * CS);
           if (separate_fixup) k_traverse_fixup<false, ExtendIO><<<grid, kBlock, 0, stream>>>(dsc, eio);
           prof_end();
           prof_begin(1);
-          k_shade<<<s->num_sms * BN_SHADE_MIN_BLOCKS, kBlock, 0, stream>>>(s->d, wp, b, A, A + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
+          k_shade<<<s->num_sms * BN_SHADE_MIN_BLOCKS, kBlock, 0, stream>>>(s->d, wp, b, S, S + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
                                                s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b * CS, n_active + (b + 1) * CS, n_shadow + b * CS,
-                                               cursors + (3 * b + 1) * CS, s->shadow_ref);
+                                               cursors + (3 * b + 1) * CS, s->shadow_ref, (order_paths && b + 1 < D && b + 1 >= order_from) ? s->sort_key : nullptr, perm);
           prof_end();
           prof_begin(2);
-          const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b * CS, cursors + (3 * b + 2) * CS, DeferList{n_defer + (2 * b + 1) * CS, s->defer_list}};
+          const ShadowIO sio{s->shq, s->shq + cp, s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_shadow + b * CS, cursors + (3 * b + 2) * CS, DeferList{n_defer + (2 * b + 1) * CS, s->defer_list}, s->cand};
           launch_traverse<true>(tgrid, stream, dsc, sio, separate_fixup ? nullptr : n_done + (2 * b + 1) * CS);
           if (separate_fixup) k_traverse_fixup<true, ShadowIO><<<grid, kBlock, 0, stream>>>(dsc, sio);
           prof_end();
-          launches += separate_fixup ? 5 : 3;
+          launches += (separate_fixup ? 5 : 3) + ((BN_CAND_PREPASS && dsc.flat_tlas != nullptr) ? 2 : 0);
           std::swap(A, B);
         }
         prof_begin(3);
@@ -954,6 +1045,12 @@ int bnint::scene_from_staged(const bnint::Staged& st, const BnCamera& c, int dev
   d.n_light_inst = st.n_light_inst;
   d.all_finite = st.all_finite;
   bnconv::convert_camera(c, d.cam);
+  for (int a = 0; a < 3; ++a) {  // ray_sort.cuh: 2^m cells per axis over the TLAS root box (any finite grid is valid: the key only orders work)
+    const float lo = st.tlas.bmin[a], ext = st.tlas.bmax[a] - st.tlas.bmin[a];
+    const bool ok = std::isfinite(lo) && std::isfinite(ext) && ext > 0.f;
+    d.sort_grid.lo[a] = ok ? lo : 0.f;
+    d.sort_grid.scale[a] = ok ? (float)(1 << kSortMBits) / ext : 0.f;
+  }
   *out = s;
   return BN_OK;
 }
@@ -975,14 +1072,14 @@ int bnint::scene_film(BnScene* s, size_t len, float** out) {
 int bnint::ensure_wave(BnScene* s, size_t cap) { return ensure_wave_buffers(s, cap); }
 
 void bnint::launch_extend(BnScene* s, cudaStream_t stream, const float4* s0, const float4* s1, float4* hits, const int* n_ptr, int* cursor, int* n_defer) {
-  const ExtendIO io{s0, s1, hits, n_ptr, cursor, DeferList{n_defer, s->defer_list}};
+  const ExtendIO io{s0, s1, hits, n_ptr, cursor, DeferList{n_defer, s->defer_list}, s->cand, nullptr, nullptr, nullptr};
   launch_traverse<false>(s->num_sms * BN_TRAV_GRID_MULT, stream, s->d, io, nullptr);
   k_traverse_fixup<false, ExtendIO><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
 }
 
 void bnint::launch_shadow(BnScene* s, cudaStream_t stream, const float4* q0, const float4* q1, const float4* q2, const float4* q3, float4* rad, const int* n_ptr,
                           int* cursor, int* n_defer) {
-  const ShadowIO io{q0, q1, q2, q3, rad, n_ptr, cursor, DeferList{n_defer, s->defer_list}};
+  const ShadowIO io{q0, q1, q2, q3, rad, n_ptr, cursor, DeferList{n_defer, s->defer_list}, s->cand};
   launch_traverse<true>(s->num_sms * BN_TRAV_GRID_MULT, stream, s->d, io, nullptr);
   k_traverse_fixup<true, ShadowIO><<<s->num_sms, kBlock, 0, stream>>>(s->d, io);
 }

@@ -17,11 +17,15 @@ struct BnScene {
   size_t arena_bytes = 0;
   // wave buffers
   size_t cap = 0;
-  float4* state[2] = {nullptr, nullptr};  // 3 planes each
+  float4* state[3] = {nullptr, nullptr, nullptr};  // [0], [1]: 3 planes each; [2]: planes 0, 1 of a bounce's paths in its ordering (ray_sort.cuh)
+  uint32_t* sort_perm = nullptr;          // ray_sort.cuh: sorted slot -> queue index (cap entries)
+  uint16_t* sort_key = nullptr;           // per queued path (cap entries)
+  uint32_t* sort_bins = nullptr;          // histogram + cursors (2 x kSortBins)
   float4* hits = nullptr;
   float4* shq = nullptr;                  // 4 planes
   float4* rad = nullptr;
   int* defer_list = nullptr;              // rays deferred to the exact fix-up kernel (cap entries)
+  uint32_t* cand = nullptr;               // small-TLAS candidate word per queued ray (k_candidates; cap entries)
   int* counters = nullptr;
   size_t counters_len = 0;
   unsigned long long* shadow_ref = nullptr;

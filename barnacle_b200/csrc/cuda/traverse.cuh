@@ -34,6 +34,8 @@
 // companion fix-up kernel with trace_exact(), a plain per-lane loop that spells
 // out the minps/maxps + NaN-propagating Math.Max/Min sequence.
 #pragma once
+#include <type_traits>
+
 #include "device_scene.h"
 #include "traverse_limits.h"
 #include "vecmath.cuh"
@@ -271,7 +273,34 @@ BN_DEV void trace_lane(const DScene& sc, const float3 wo, const float3 wd, float
 //              void store(int i, const TraceResult&) ;
 //              void defer(int i)      // ray i needs the exact path (fix-up kernel)
 //              void prefetch(int i)   // hint: ray i will be loaded soon (L2 prefetch)
+// optional:    static constexpr bool kHasCand = true ; uint32_t cand(int i)
+//              the small-TLAS candidate word of ray i, computed beforehand by candidate_word() in a full-width
+//              pre-pass (kernels.cu: k_candidates) instead of by the refilled lanes of this loop
 // ---------------------------------------------------------------------------------
+constexpr uint32_t kCandDefer = 0x80000000u;  // candidate word: the ray does not qualify for the fast slab form
+template <class IO, class = void> struct io_has_cand : std::false_type {};
+template <class IO> struct io_has_cand<IO, std::void_t<decltype(IO::kHasCand)>> : std::bool_constant<IO::kHasCand> {};
+
+// Small TLAS: ONE uniform pass over the octant-ordered instance boxes with the initial t gives the candidate set
+// (bit k = k-th instance in visiting order).  t only shrinks, so an instance that fails now fails later too; candidates
+// are re-checked against the then-current t when their turn comes (phase S), which is the reference's test.
+BN_DEV uint32_t candidate_mask(const DScene& sc, const float3 wo, const float3 winv, const uint32_t wsigns, const float t) {
+  const uint32_t n_inst = sc.n_inst;
+  const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns & 7u) * n_inst);
+  uint32_t mask = 0u;
+  for (uint32_t k = 0; k < n_inst; ++k) {
+    BN_WORK(25);
+    const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
+    if (flat_pass(a, b, wo, winv, t)) mask |= 1u << k;
+  }
+  return mask;
+}
+// The word the pre-pass stores per ray: kCandDefer, or the candidate mask (n_inst <= 16: bits 0..15).
+BN_DEV uint32_t candidate_word(const DScene& sc, const float3 wo, const float3 wd, const float t) {
+  const float3 winv = rcp3(wd);
+  if (!(sc.all_finite != 0u && slab_fast_ok(wo, winv))) return kCandDefer;
+  return candidate_mask(sc, wo, winv, dir_signs(wd), t);
+}
 // `cold`: this thread's column of a [kTravColdWords][blockDim.x] shared-memory array.  The state a
 // ray touches a few times in its life (committed hit, queue slot, world direction, candidate mask)
 // lives there instead of in registers; that is what lets the kernel fit 9 CTAs per SM.
@@ -391,28 +420,39 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         o = wo; d = wd; inv = winv; signs = wsigns;
         in_obj = false; cur_inst = -1; sp = 0; tri_k = 0; tl_pos = 0;
         h_inst = -1; h_prim = -1; h_u = 0.f; h_v = 0.f;
-        if (!(scene_fast && slab_fast_ok(wo, winv))) {
-          io.defer(index);
-        } else if (flat) {
-          // Small TLAS: ONE uniform pass over the octant-ordered instance boxes with the initial t
-          // gives the candidate set (bit k = k-th instance in visiting order).  t only shrinks, so
-          // an instance that fails now fails later too; candidates are re-checked against the
-          // then-current t when their turn comes (phase S), which is the reference's test.
-          const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns & 7u) * n_inst);
-          uint32_t mask = 0u;
-          for (uint32_t k = 0; k < n_inst; ++k) {
-            BN_WORK(25);
-            const float4 a = __ldg(fp + 2u * k), b = __ldg(fp + 2u * k + 1u);
-            if (flat_pass(a, b, wo, winv, t)) mask |= 1u << k;
+        // what the refilled lane does when nobody has looked at its ray yet (flat_scan: the scene has a small TLAS)
+        auto start_ray = [&](const bool flat_scan) {
+          if (!(scene_fast && slab_fast_ok(wo, winv))) {
+            io.defer(index);
+          } else if (flat_scan) {
+            const uint32_t mask = candidate_mask(sc, wo, winv, wsigns, t);
+            tl_pos = mask;
+            if (mask) cur = kScan;
+            else finish();
+          } else {
+            // BVHAggregate pops node 0 and tests its bounds first (BVH.fs:45-47)
+            const Slab s = slab<true>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv);
+            if (slab_pass<true>(s, t)) cur = (WIDE ? sc.tlas_wroot : sc.tlas.root) | kTlasBit;
+            else finish();
           }
-          tl_pos = mask;
-          if (mask) cur = kScan;
-          else finish();
+        };
+        if constexpr (io_has_cand<IO>::value) {
+          if (flat) {
+            // the pre-pass has run the fast-form check and the candidate pass for this ray (k_candidates: all 32 lanes
+            // of its warps busy, where the refilled lanes of this loop are 14-20 of 32)
+            const uint32_t m = io.cand(mine);
+            if (m & kCandDefer) {
+              io.defer(index);
+            } else {
+              tl_pos = m;
+              if (m) cur = kScan;
+              else finish();
+            }
+          } else {
+            start_ray(false);
+          }
         } else {
-          // BVHAggregate pops node 0 and tests its bounds first (BVH.fs:45-47)
-          const Slab s = slab<true>(f3(sc.tlas.bmin[0], sc.tlas.bmin[1], sc.tlas.bmin[2]), f3(sc.tlas.bmax[0], sc.tlas.bmax[1], sc.tlas.bmax[2]), o, inv);
-          if (slab_pass<true>(s, t)) cur = (WIDE ? sc.tlas_wroot : sc.tlas.root) | kTlasBit;
-          else finish();
+          start_ray(flat);
         }
       }
       continue;  // re-vote with the new rays

@@ -8,7 +8,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cbox_bunny"
 scene = Scene.Load(os.path.join(ROOT, "scenes", name + ".json"), base_dir=ROOT)
 g = scene.gpu(); o = OracleScene(scene.desc)
 W = 1024
-rays = o.primary_rays(make_params(W, W, 2))            # pixel-major order within sample: coherent
+rays = o.primary_rays(make_params(W, W, int(os.environ.get("SORT_SPP", "8"))))            # pixel-major order within sample: coherent
 hits = g.trace(rays)
 ok = hits["instance"] >= 0
 rng = np.random.Generator(np.random.PCG64(3))
@@ -46,6 +46,22 @@ for nm, b in (("primary", rays), ("secondary", sec), ("tertiary", ter)):
     run(b, "as generated")
     octant = (b["direction"][:, 0] > 0).astype(np.uint32) | ((b["direction"][:, 1] > 0).astype(np.uint32) << 1) | ((b["direction"][:, 2] > 0).astype(np.uint32) << 2)
     run(b[np.argsort(octant, kind="stable")], "octant (stable)")
+    # what producer-side binning into per-octant chunks would give: a chunk is opened by the first ray that needs it and
+    # consumed in the order the chunks were opened
+    for CH in (256, 1024, 4096):
+        rank = np.zeros(len(b), np.int64)
+        for oc in range(8):
+            m = octant == oc
+            rank[m] = np.arange(m.sum())
+        chunk = rank // CH
+        key_open = np.zeros(len(b), np.int64)
+        for oc in range(8):
+            m = np.flatnonzero(octant == oc)
+            if len(m) == 0: continue
+            first = m[::CH]                      # stream position of the ray that opens each chunk
+            key_open[m] = first[chunk[m]]
+        run(b[np.lexsort((rank, key_open))], f"octant chunks of {CH}")
+    run(b[np.argsort((octant << 9) | morton(b["origin"], 3), kind="stable")], "octant + morton9")
     run(b[np.argsort((octant << 15) | morton(b["origin"]), kind="stable")], "octant + morton15")
     run(b[np.argsort(morton(b["origin"]), kind="stable")], "morton15 only")
     run(b[rng.permutation(len(b))], "random shuffle")
