@@ -49,10 +49,10 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;  // lane idle (a leaf ref that no scene 
 constexpr uint32_t kScan = 0xFFFFFFFEu;  // lane is at the small-TLAS ordered scan (ditto)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef BN_REFILL_MIN
-#define BN_REFILL_MIN 14
+#define BN_REFILL_MIN 20   // (14 before the paths were ordered between bounces; re-swept on ordered rays: profiles/r02_ab_session18_*.log)
 #endif
 #ifndef BN_REFILL_MIN_ANY
-#define BN_REFILL_MIN_ANY 16
+#define BN_REFILL_MIN_ANY 20
 #endif
 constexpr int kRefillMin = BN_REFILL_MIN;  // refill when at least this many lanes are idle
 constexpr int kRefillMinAny = BN_REFILL_MIN_ANY;  // ... for any-hit (shadow) rays
