@@ -168,9 +168,11 @@ struct ExtendIO {
   BN_DEV int* cursor() const { return cur; }
   BN_DEV void load(int i, float3& o, float3& d, float& t) const {
     if (perm) {
-      const int src = (int)perm[i];
-      const float4 a = s0[src], b = s1[src];
-      t0[i] = a; t1[i] = b;
+      // past L1 (ld.global.cg) and streaming stores: neither the gathered records nor the ordered copies are read again by
+      // this kernel (neutral to +1 %, profiles/r02_ab_session21_*.log)
+      const int src = (int)__ldcg(perm + i);
+      const float4 a = __ldcg(s0 + src), b = __ldcg(s1 + src);
+      __stcs(t0 + i, a); __stcs(t1 + i, b);
       o = f3(a.x, a.y, a.z); d = f3(a.w, b.x, b.y);
     } else {
       const float4 a = s0[i], b = s1[i];
@@ -188,7 +190,7 @@ struct ExtendIO {
       // two stages: the perm line one more window ahead (32 entries per 128-B line), and through the entry that an earlier
       // refill prefetched, the state it points at
       if ((i & 31) == 0 && i + kPrefetchAhead < *n_ptr) prefetch_l2(perm + i + kPrefetchAhead);
-      const int src = (int)perm[i];
+      const int src = (int)__ldcg(perm + i);
       prefetch_l2(s0 + src); prefetch_l2(s1 + src);
     } else {
       prefetch_l2(s0 + i); prefetch_l2(s1 + i);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
     float3 sh_wi = splat(0.f), sh_a = splat(0.f), sh_b = splat(0.f);
     float sh_tmax = 0.f;
     if (i < n) {
-      const float4 a = s0[i], b = s1[i], c = s2[perm ? (int)perm[i] : i], h = hits[i];  // third plane: where the previous shade left it (ray_sort.cuh)
+      const float4 a = s0[i], b = s1[i], c = perm ? __ldcg(s2 + __ldcg(perm + i)) : s2[i], h = hits[i];  // third plane: where the previous shade left it (ray_sort.cuh)
       shade_lane(sc, wp.integrator, wp.rr_depth, wp.max_depth, wp.flags, bounce, a, b, c, h, rad, alive, has_shadow, ref_shadow, P, nd, beta, bs_pdf, rng, pid,
                  sh_wi, sh_a, sh_b, sh_tmax);
     }

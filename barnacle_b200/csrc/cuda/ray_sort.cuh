@@ -41,8 +41,12 @@ namespace bn {
 constexpr int kSortMBits = BN_SORT_MBITS;
 constexpr int kSortBins = 8 << (3 * kSortMBits);
 constexpr int kSortThreads = 256;
-constexpr int kSortPerThread = 16;
+#ifndef BN_SORT_PER_THREAD
+#define BN_SORT_PER_THREAD 16
+#endif
+constexpr int kSortPerThread = BN_SORT_PER_THREAD;
 constexpr int kSortTile = kSortThreads * kSortPerThread;  // 4096 paths: a rank fits 16 bits next to a 12-bit key
+static_assert(kSortTile <= 65536, "a rank within a tile must fit 16 bits");
 static_assert(kSortBins <= 4096 && kSortMBits >= 0, "the sort key must fit 12 bits");
 
 // key = octant of the direction (the small-TLAS scan order and the child order of every node depend on it) above the

@@ -398,6 +398,12 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
     const int n_idle = 32 - (nN + nT + nE + nS);
 
     // ---- refill idle lanes from the queue
+    // Each refill claims exactly the slots it fills, at the cursor's position of that moment.  (Measured and dropped,
+    // profiles/r02_ab_session22_*.log, r02_ab_session23_*.log: holding claimed blocks / chunks of 64-256 consecutive slots per
+    // warp with the next atomic in flight, so that no refill waits for the cursor's round trip — ncu's top long-scoreboard
+    // stall, 10 % of the samples.  C1 +3.5 %, but C2 -7 %, C3 -5 %, C4 -7 %, and worse the more a warp claims ahead: with
+    // exact claims all warps of the GPU walk ONE narrow front through the ordered queue, i.e. through the same cell of the
+    // scene, and that is what keeps the node records in L1.)
     if (n_idle != 0 && !exhausted && (n_idle >= (ANY ? kRefillMinAny : kRefillMin) || n_idle == 32)) {
       const unsigned idle = __ballot_sync(kFull, cur == kNone);
       int base = 0;

@@ -39,6 +39,7 @@ static inline unsigned __ballot_sync(unsigned, int p) { return hostsim_warp_sync
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)hostsim_warp_sync(2, (unsigned)v, src); }
 static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return hostsim_warp_sync(2, v, src); }
 static inline float __shfl_sync(unsigned, float v, int src) { return __uint_as_float(hostsim_warp_sync(2, __float_as_uint(v), src)); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { (void)hostsim_warp_sync(1, 0u, 0); }  // a rendezvous like any other (a ballot nobody reads)
 struct HostsimLaneX { operator unsigned() const { return hostsim_lane_id(); } };
 struct HostsimThreadIdx { HostsimLaneX x; unsigned y = 0, z = 0; };
 static HostsimThreadIdx threadIdx;
@@ -46,6 +47,7 @@ static HostsimThreadIdx threadIdx;
 static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
 struct HostsimThreadIdx { unsigned x = 0, y = 0, z = 0; };
 static HostsimThreadIdx threadIdx;
 #endif

@@ -27,5 +27,7 @@ timeout 400 ncu --set full --clock-control none -k regex:^k_traverse$ -s 2 -c 2 
   python bench.py --workload C4 --spp 8 --steps 1 --warmup 0 --no-cpu-baseline --no-configs > gpurun_out/${TAG}_prof_traverse_C4.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:^k_shade$ -s 1 -c 1 -o gpurun_out/${TAG}_shade -f \
   python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-configs > gpurun_out/${TAG}_prof_shade.log 2>&1
+timeout 200 ncu --set full --clock-control none -k regex:^k_sort_ -s 3 -c 3 -o gpurun_out/${TAG}_sort -f \
+  python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-configs > gpurun_out/${TAG}_prof_sort.log 2>&1
 ls -la gpurun_out | grep ${TAG}_ | awk '{print $5, $9}'
 echo "== done after $(( $(date +%s) - T0 )) s"
