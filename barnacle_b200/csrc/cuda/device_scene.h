@@ -138,7 +138,7 @@ struct GCamera {
 };
 
 // Grid of the path re-ordering between bounces (ray_sort.cuh): cell = clamp(int((p - lo) * scale), 0, 2^m - 1) per axis
-struct SortGrid { float lo[3]; float scale[3]; };
+struct SortGrid { float lo[3]; float scale[3]; uint32_t cell_major; uint32_t pad; };  // cell_major: key = cell above octant (scenes behind a small TLAS)
 
 struct DScene {
   const GNode* nodes;        // TLAS nodes first, then every mesh's nodes

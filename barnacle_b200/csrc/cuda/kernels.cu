@@ -1047,6 +1047,8 @@ int bnint::scene_from_staged(const bnint::Staged& st, const BnCamera& c, int dev
   d.n_light_inst = st.n_light_inst;
   d.all_finite = st.all_finite;
   bnconv::convert_camera(c, d.cam);
+  d.sort_grid.cell_major = d.flat_tlas != nullptr ? 1u : 0u;
+  d.sort_grid.pad = 0u;
   for (int a = 0; a < 3; ++a) {  // ray_sort.cuh: 2^m cells per axis over the TLAS root box (any finite grid is valid: the key only orders work)
     const float lo = st.tlas.bmin[a], ext = st.tlas.bmax[a] - st.tlas.bmin[a];
     const bool ok = std::isfinite(lo) && std::isfinite(ext) && ext > 0.f;

@@ -49,7 +49,7 @@ constexpr int kSortTile = kSortThreads * kSortPerThread;  // 4096 paths: a rank 
 static_assert(kSortTile <= 65536, "a rank within a tile must fit 16 bits");
 static_assert(kSortBins <= 4096 && kSortMBits >= 0, "the sort key must fit 12 bits");
 
-// key = octant of the direction (the small-TLAS scan order and the child order of every node depend on it) above the
+// key = octant of the direction (the small-TLAS scan order and the child order of every node depend on it) and the
 // Morton code of the origin's cell.  Any value is a valid key: a NaN origin lands in cell 0.
 BN_DEV uint32_t sort_key(const SortGrid& g, const float3 p, const float3 d) {
   const int m = (1 << kSortMBits) - 1;
@@ -61,7 +61,11 @@ BN_DEV uint32_t sort_key(const SortGrid& g, const float3 p, const float3 d) {
   for (int b = 0; b < kSortMBits; ++b)
     code |= (((uint32_t)qx >> b) & 1u) << (3 * b) | (((uint32_t)qy >> b) & 1u) << (3 * b + 1) | (((uint32_t)qz >> b) & 1u) << (3 * b + 2);
   const uint32_t oct = (d.x > 0.f ? 1u : 0u) | (d.y > 0.f ? 2u : 0u) | (d.z > 0.f ? 4u : 0u);
-  return (oct << (3 * kSortMBits)) | code;
+  // octant-major: neighbours in the queue share the octant and lie in neighbouring cells; cell-major: they share the cell.
+  // Measured (profiles/r02_ab_session24_*.log): cell-major C1 -2.8 %, C2 -1.8 % per frame (scenes behind a small TLAS: every
+  // octant scans the same <= 16 instance boxes, a cell's rays share the BLAS regions they enter), C3 +1.3 %, C4 -0.2 % (tree
+  // TLAS: the octant decides which half of every node comes first) — so the layout follows the scene (SortGrid.cell_major).
+  return g.cell_major ? (code << 3) | oct : (oct << (3 * kSortMBits)) | code;
 }
 
 __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint16_t* __restrict__ key, const int* __restrict__ n_ptr, uint32_t* __restrict__ hist) {
