@@ -198,3 +198,40 @@ def test_pbr_pdf_is_a_density():
         upper = 4 * math.pi * np.where(wis[:, 2] > 0, pdf, 0).mean()
         assert whole == pytest.approx(1 + w_cos, rel=0.04), (metallic, roughness, whole)
         assert 0.7 < upper < 1.03, (metallic, roughness, upper)  # rough lobes lose up to ~a quarter below the horizon
+
+
+@pytest.mark.parametrize("metallic,roughness", [(0.0, 0.4), (1.0, 0.3), (0.5, 0.6), (0.0, 0.8)])
+def test_pbr_directional_albedo_furnace(metallic, roughness):
+    """White-furnace-style check of PBRMaterial that needs no rendered sphere (the published renders' sphere was made with another
+    roughness): the directional albedo a(wo) = integral of Eval(wo, wi).bsdf over the UPPER hemisphere (the bsdf
+    carries its cosine, PBR.fs:37-46), computed twice —
+      (i)  by quadrature over (theta, phi) of the independent float64 restatement of PBR.fs above, and
+      (ii) as the importance-sampling estimate mean(bsdf / pdf) over the oracle's own Sample draws that land in the upper
+           hemisphere (what PathTracingIntegrator.Li multiplies the throughput by, PathTracing.fs:61-67).
+    (ii) is unbiased for (i) only if Sample's directions are distributed with the density Eval reports AND Eval's bsdf is the
+    restated formula: lobe selection, the half-vector pdf's Jacobian, D, G and the Fresnel mixes all enter.  A white base colour
+    bounds the energy: a(wo) <= 1 up to the known excess of the un-normalised diffuse + specular mix, asserted as < 1.15."""
+    rng = np.random.default_rng(11)
+    base = np.array([1.0, 1.0, 1.0])
+    alpha = float(max(np.float32(roughness) * np.float32(roughness), np.float32(1e-3)))
+    m = _material(_ffi.BN_MAT_PBR, base, p0=metallic, p1=alpha)
+    for cos_o in (0.95, 0.6, 0.3):
+        wo = np.array([math.sqrt(1 - cos_o * cos_o), 0.0, cos_o])
+        # (i) midpoint quadrature in (cos theta, phi), denser near the specular peak than a uniform grid needs: 400 x 720
+        ct = (np.arange(400) + 0.5) / 400
+        ph = (np.arange(720) + 0.5) / 720 * 2 * math.pi
+        quad = 0.0
+        for c in ct:
+            s = math.sqrt(1 - c * c)
+            wis = np.stack([s * np.cos(ph), s * np.sin(ph), np.full_like(ph, c)], axis=1)
+            quad += sum(ref_pbr_eval(base, metallic, alpha, wo, wi)[0][0] for wi in wis[::8]) * 8
+        quad *= (1 / 400) * (2 * math.pi / 720)
+        # (ii) the oracle's Sample / Eval
+        est, n = 0.0, 20000
+        for ul, u in zip(rng.random(n), rng.random((n, 2))):
+            sres = oracle_ffi.material_sample(m, wo, ul, u)
+            if sres[6] > 0 and sres[3] > 0:  # upper hemisphere, pdf > 0
+                est += sres[0] / sres[3]
+        est /= n
+        assert est == pytest.approx(quad, rel=0.05), (metallic, roughness, cos_o, est, quad)
+        assert 0.0 < quad < 1.15, (metallic, roughness, cos_o, quad)
