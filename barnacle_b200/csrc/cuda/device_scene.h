@@ -52,10 +52,11 @@ static_assert(sizeof(GNode) == 64, "GNode must be 64 B");
 // whatever the number of active lanes); the swizzle spreads a warp's loads over the eight bank groups.  Measured on the
 // B200 (profiles/r02_ab_session4_swizzle.log): the L1 data pipe of the extend launches falls from 80-83 % to 74-75 % busy —
 // and the frame time does not move (C1 -1.0 %, C2 -1.4 %, C3 +0.8 %, C4 +1.8 %): the kernel is bound by instruction issue
-// (76 %), not by L1, and the swizzle costs two instructions per node step.  Kept as a switch; the struct below is the
-// LOGICAL layout.
+// (76 %), not by L1, and the swizzle costs two instructions per node step.  Once the paths were ordered between bounces
+// (ray_sort.cuh) the kernel was no longer bound by issue slots and the relieved L1 pipe showed (profiles/r02_ab_session26_*.log:
+// C2 extend -2.7 %, C4 frame -2.3 %, C1 / C3 equal): ON by default since.  The struct below is the LOGICAL layout.
 #ifndef BN_WIDE_SWIZZLE
-#define BN_WIDE_SWIZZLE 0
+#define BN_WIDE_SWIZZLE 1
 #endif
 struct __align__(128) GWide {
   float lo[3][4];    //   +0: lo.x of slots 0..3 | +16: lo.y | +32: lo.z

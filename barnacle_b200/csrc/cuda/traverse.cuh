@@ -71,6 +71,11 @@ constexpr int kRefillMinAny = BN_REFILL_MIN_ANY;  // ... for any-hit (shadow) ra
 #ifndef BN_WIDE_LDG256
 #define BN_WIDE_LDG256 0   // 1: a 4-wide node is fetched with four 256-bit loads instead of eight 128-bit ones
 #endif
+#ifndef BN_SPLIT_REFILL
+#define BN_SPLIT_REFILL 0   // 1: split-phase refill — the cursor's atomic is issued at one vote and its result used at the next, with ONE
+                            // phase step of the lanes that still hold a ray in between (the claim stays exact: the lanes idle at the
+                            // first vote get the slots)
+#endif
 #ifndef BN_PREFETCH_AHEAD
 #define BN_PREFETCH_AHEAD 16384
 #endif
@@ -357,6 +362,10 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   bool exhausted = false;
+#if BN_SPLIT_REFILL
+  unsigned pend_mask = 0u;  // lanes that get the slots of the claim in flight (0: none)
+  int pend_base = 0;        // lane 0: the atomic's result
+#endif
   const bool scene_fast = sc.all_finite != 0u;
   const bool flat = sc.flat_tlas != nullptr;
   const uint32_t n_inst = sc.n_inst;
@@ -404,6 +413,22 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
     // stall, 10 % of the samples.  C1 +3.5 %, but C2 -7 %, C3 -5 %, C4 -7 %, and worse the more a warp claims ahead: with
     // exact claims all warps of the GPU walk ONE narrow front through the ordered queue, i.e. through the same cell of the
     // scene, and that is what keeps the node records in L1.)
+#if BN_SPLIT_REFILL
+    bool claimed_now = false;
+    if (pend_mask == 0u && n_idle != 0 && !exhausted && (n_idle >= (ANY ? kRefillMinAny : kRefillMin) || n_idle == 32)) {
+      pend_mask = __ballot_sync(kFull, cur == kNone);
+      if (lane == 0) pend_base = atomicAdd(io.cursor(), n_idle);
+      claimed_now = n_idle != 32;  // lanes with a ray left: one phase step while the atomic is in flight
+    }
+    if (pend_mask != 0u && !claimed_now) {
+      const unsigned idle = pend_mask;
+      const int claimed = __popc(idle);
+      pend_mask = 0u;
+      const int base = __shfl_sync(kFull, pend_base, 0);
+      if (base + claimed >= n) exhausted = true;
+      const int mine = base + __popc(idle & lt_mask);
+      if (((idle >> lane) & 1u) && mine < n) {
+#else
     if (n_idle != 0 && !exhausted && (n_idle >= (ANY ? kRefillMinAny : kRefillMin) || n_idle == 32)) {
       const unsigned idle = __ballot_sync(kFull, cur == kNone);
       int base = 0;
@@ -412,6 +437,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
       if (base + n_idle >= n) exhausted = true;
       const int mine = base + __popc(idle & lt_mask);
       if (cur == kNone && mine < n) {
+#endif
         index = mine;
         // Claims tile the queue in increasing order, so "my slot + kPrefetchAhead" is a ray some
         // warp will claim about a DRAM latency from now: every refill pulls its share of that
@@ -463,7 +489,12 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
       }
       continue;  // re-vote with the new rays
     }
+#if BN_SPLIT_REFILL
+    if (n_idle == 32 && pend_mask == 0u) break;  // nothing in flight, nothing claimed, and the queue is exhausted
+    if (n_idle == 32) continue;
+#else
     if (n_idle == 32) break;  // nothing in flight and the queue is exhausted
+#endif
     BN_STAT(3, 32 - n_idle);
 
     if (nN >= nT && nN >= nE && nN >= nS) {
@@ -576,6 +607,9 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
           }
         }
         if (__popc(__ballot_sync(kFull, (int)cur >= 0)) < kStayMin) break;
+#if BN_SPLIT_REFILL
+        if (pend_mask != 0u) break;
+#endif
 #ifdef BN_EXP_STAY_REFILL
         // experiment queued for the next GPU session (default off): closest-hit rays in tree-TLAS scenes leave
         // the stay loop as soon as a refill is due (BN_EXP_STAY_REFILL idle lanes), instead of stepping on with those lanes empty
@@ -611,6 +645,9 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
           }
         }
         if (__popc(__ballot_sync(kFull, (cur >> 30) == 2u)) < kStayT) break;
+#if BN_SPLIT_REFILL
+        if (pend_mask != 0u) break;
+#endif
 #ifdef BN_EXP_STAY_REFILL
         if (!ANY && !flat && !exhausted && __popc(__ballot_sync(kFull, cur == kNone)) >= BN_EXP_STAY_REFILL) break;
 #endif

@@ -353,10 +353,11 @@ def test_unordered_any_hit_experiment_gives_the_same_answers(warp_any_unordered,
     _check_persistent_loop(warp_any_unordered, Scene.LoadString(_random_scene_json(np.random.default_rng(62), 40)), 2000, seed=62)
 
 
-@pytest.mark.parametrize("tag,defines", [("_swz", ["BN_WIDE_SWIZZLE=1"]), ("_swz256", ["BN_WIDE_SWIZZLE=1", "BN_WIDE_LDG256=1"]), ("_ldg256", ["BN_WIDE_LDG256=1"])])
+@pytest.mark.parametrize("tag,defines", [("_noswz", ["BN_WIDE_SWIZZLE=0"]), ("_swz256", ["BN_WIDE_SWIZZLE=1", "BN_WIDE_LDG256=1"]), ("_ldg256", ["BN_WIDE_SWIZZLE=0", "BN_WIDE_LDG256=1"])])
 def test_wide_node_layout_switches_give_the_same_hits(root, scene_loader, lib, tag, defines):
-    """The bank-swizzled node layout (-DBN_WIDE_SWIZZLE=1: chunk j of node i at j ^ (i & 7), converter and kernel agree) and the
-    256-bit node fetch (-DBN_WIDE_LDG256=1), measured on the B200 and left off: same hits, same any-hit answers."""
+    """The bank-swizzled node layout (BN_WIDE_SWIZZLE: chunk j of node i at j ^ (i & 7), converter and kernel agree; the default
+    since the paths are ordered between bounces) against the plain layout (-DBN_WIDE_SWIZZLE=0), and the 256-bit node fetch
+    (-DBN_WIDE_LDG256=1, measured on the B200 and left off) on either: same hits, same any-hit answers."""
     variant = _build_warp_emulator(root, tag, defines)
     for name in ("cbox_bunny", "material_sweep", "bunny_instanced_small"):
         _check_persistent_loop(variant, scene_loader(name), 2500, seed=91)
@@ -394,3 +395,14 @@ def test_whole_paths_on_randomised_scenes(hs, lib, oracle_lib, seed, n_instances
     want_film, st = oracle.render(p, threads=1, counters=True)
     assert _bits_equal(film, want_film) and (np.nan_to_num(film).sum(axis=1) > 0).mean() > 0.05
     assert n_ext == st["extend_rays"] and n_sh == st["shadow_rays_nonnull"]
+
+
+
+def test_split_phase_refill_gives_the_same_hits(root, scene_loader, lib):
+    """-DBN_SPLIT_REFILL=1 (measured on the B200): the cursor's atomic issued at one vote, its result used at the
+    next, ONE phase step of the lanes that still hold a ray in between; the claim stays exact.  Every ray is traced exactly once
+    and the hits are the oracle's."""
+    variant = _build_warp_emulator(root, "_split_refill", ["BN_SPLIT_REFILL=1"])
+    for name in ("cbox_pt", "cbox_bunny", "material_sweep", "bunny_instanced_small"):
+        _check_persistent_loop(variant, scene_loader(name), 2500, seed=61)
+    _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(62), 60)), 2000, seed=62)
