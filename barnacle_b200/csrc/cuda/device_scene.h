@@ -70,12 +70,29 @@ struct __align__(128) GWide {
 static_assert(sizeof(GWide) == 128, "GWide must be 128 B");
 constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
 
+// BN_TRI64 (switch, off): the record padded to 64 B so that the closest-hit kernel fetches a triangle with TWO 256-bit loads
+// instead of three 128-bit ones (a gathered load costs the L1 data pipe a lane-cycle whatever its width,
+// profiles/r02_l1_gather_microbench.txt).  Measured on the ordered kernel (profiles/r02_ab_session28_*.log): C2 extend
+// 24.87 -> 25.03 ms, C1 / C3 / C4 within 0.2 % — the wavefronts saved are lost again to a third more triangle bytes in L1.
+#ifndef BN_TRI64
+#define BN_TRI64 0
+#endif
+#if BN_TRI64
+struct __align__(32) GTri {  // pre-gathered vertices of one BLAS-order triangle
+  float p0[3]; float pad0;
+  float p1[3]; float pad1;
+  float p2[3]; float pad2;
+  float pad3[4];
+};
+static_assert(sizeof(GTri) == 64, "GTri must be 64 B");
+#else
 struct __align__(16) GTri {  // pre-gathered vertices of one BLAS-order triangle
   float p0[3]; float pad0;
   float p1[3]; float pad1;
   float p2[3]; float pad2;
 };
 static_assert(sizeof(GTri) == 48, "GTri must be 48 B");
+#endif
 
 struct __align__(16) GTree {  // root of a TLAS / BLAS
   float bmin[3]; uint32_t root;       // root ref (a leaf ref if the tree is a single leaf / single instance)

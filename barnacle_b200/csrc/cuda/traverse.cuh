@@ -625,9 +625,17 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         if ((cur >> 30) == 2u) {
           const uint32_t count = (cur >> 27) & 7u;
           const uint32_t tri = (cur & kFirstMask) + tri_k;
-          const float4* tp4 = tri_base + (size_t)tri * 3u;
-          const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
-          const float3 p0 = f3(a.x, a.y, a.z), p1 = f3(b.x, b.y, b.z), p2 = f3(c.x, c.y, c.z);
+          float3 p0, p1, p2;
+          if (BN_TRI64 && !ANY) {
+            // two 32-B loads (device_scene.h: GTri; a measured switch, off)
+            const uintptr_t tri_at = reinterpret_cast<uintptr_t>(tri_base) + (size_t)tri * sizeof(GTri);
+            const F8 c0 = ldg256(tri_at), c1 = ldg256(tri_at + 32u);
+            p0 = f3(c0.v[0], c0.v[1], c0.v[2]); p1 = f3(c0.v[4], c0.v[5], c0.v[6]); p2 = f3(c1.v[0], c1.v[1], c1.v[2]);
+          } else {
+            const float4* tp4 = tri_base + (size_t)tri * (sizeof(GTri) / 16u);
+            const float4 a = __ldg(tp4), b = __ldg(tp4 + 1), c = __ldg(tp4 + 2);
+            p0 = f3(a.x, a.y, a.z); p1 = f3(b.x, b.y, b.z); p2 = f3(c.x, c.y, c.z);
+          }
           // Triangle.Bounds (Mesh.fs:19-22): finite vertices => fmin/fmax == minps/maxps
           const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
           const float3 hi = f3(fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z));
@@ -726,7 +734,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
               const float3 wd = f3(wdx, wdy, wdz);
               bool occluded = false;
               for (uint32_t j = 0; j < count; ++j) {
-                const float4* tp4 = tri_base + (size_t)(first + j) * 3u;
+                const float4* tp4 = tri_base + (size_t)(first + j) * (sizeof(GTri) / 16u);
                 const float4 ta = __ldg(tp4), tb = __ldg(tp4 + 1), tc = __ldg(tp4 + 2);
                 const float3 p0 = f3(ta.x, ta.y, ta.z), p1 = f3(tb.x, tb.y, tb.z), p2 = f3(tc.x, tc.y, tc.z);
                 const float3 lo = f3(fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z));
