@@ -269,19 +269,36 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
                                                   const float4* __restrict__ s2, const float4* __restrict__ hits, float4* __restrict__ o0,
                                                   float4* __restrict__ o1, float4* __restrict__ o2, float4* __restrict__ q0, float4* __restrict__ q1,
                                                   float4* __restrict__ q2, float4* __restrict__ q3, float4* __restrict__ rad, const int* __restrict__ n_ptr,
-                                                  int* n_out, int* n_shadow, int* cursor, unsigned long long* shadow_ref, uint16_t* __restrict__ key_out, const uint32_t* __restrict__ perm) {
+                                                  int* n_out, int* cursor, unsigned long long* shadow_ref, uint16_t* __restrict__ key_out, const uint32_t* __restrict__ perm) {
+  // n_out: the next bounce's path counter; n_out + 1: this bounce's shadow-queue counter (one 8-byte word, see the append below)
   const int n = *n_ptr;
   unsigned ref_total = 0;  // lane 0: reference-equivalent shadow rays of this warp's chunks
-  int next = warp_fetch(cursor);
+  // Claim pipeline, three chunks of 32 paths deep, so that nothing on this loop's critical path waits for a round trip it
+  // could have started earlier (ncu on the ordered kernel: the shuffle behind the cursor's atomic and the permutation entry
+  // in front of the third plane's gather were 12 % of the stall samples):
+  //   chunk c0: shaded now | chunk c1: its inputs prefetched into L2 now, through the permutation entries fetched an
+  //   iteration ago | chunk c2: its base comes out of the atomic issued an iteration ago, its permutation entries are
+  //   fetched now | the atomic for the chunk after that is issued now.
+  const int lane = lane_id();
+  auto order = [&](int j) { return (perm && j < n) ? (int)__ldcg(perm + j) : j; };
+  int raw = 0;
+  if (lane == 0) raw = atomicAdd(cursor, 96);
+  int c0 = __shfl_sync(0xffffffffu, raw, 0), c1 = c0 + 32;
+  raw = c0 + 64;
+  int src0 = order(c0 + lane), src1 = order(c1 + lane);
   for (;;) {
-    const int base = next;
+    const int base = c0;
     if (base >= n) break;
-    next = warp_fetch(cursor);  // claimed one chunk ahead: the atomic's round trip overlaps this chunk's shading
-    if (next + lane_id() < n) {  // ... and so does the DRAM latency of its inputs
-      const int j = next + lane_id();
-      prefetch_l2(s0 + j); prefetch_l2(s1 + j); prefetch_l2(s2 + (perm ? (int)perm[j] : j)); prefetch_l2(hits + j);
+    const int c2 = __shfl_sync(0xffffffffu, raw, 0);
+    if (lane == 0) raw = atomicAdd(cursor, 32);
+    const int src2 = order(c2 + lane);
+    if (c1 + lane < n) {
+      const int j = c1 + lane;
+      prefetch_l2(s0 + j); prefetch_l2(s1 + j); prefetch_l2(s2 + src1); prefetch_l2(hits + j);
     }
-    const int i = base + lane_id();
+    const int src = src0;
+    c0 = c1; c1 = c2; src0 = src1; src1 = src2;
+    const int i = base + lane;
     bool alive = false, has_shadow = false, ref_shadow = false;
     float3 P = splat(0.f), nd = splat(0.f), beta = splat(0.f);
     float bs_pdf = 0.f;
@@ -290,18 +307,26 @@ __global__ void __launch_bounds__(kBlock, BN_SHADE_MIN_BLOCKS) k_shade(DScene sc
     float3 sh_wi = splat(0.f), sh_a = splat(0.f), sh_b = splat(0.f);
     float sh_tmax = 0.f;
     if (i < n) {
-      const float4 a = s0[i], b = s1[i], c = perm ? __ldcg(s2 + __ldcg(perm + i)) : s2[i], h = hits[i];  // third plane: where the previous shade left it (ray_sort.cuh)
+      const float4 a = s0[i], b = s1[i], c = perm ? __ldcg(s2 + src) : s2[i], h = hits[i];  // third plane: where the previous shade left it (ray_sort.cuh)
       shade_lane(sc, wp.integrator, wp.rr_depth, wp.max_depth, wp.flags, bounce, a, b, c, h, rad, alive, has_shadow, ref_shadow, P, nd, beta, bs_pdf, rng, pid,
                  sh_wi, sh_a, sh_b, sh_tmax);
     }
-    const int pos = warp_append(n_out, alive);
+    // both appends with ONE atomic: the shadow-queue counter is the int right after the path counter (render_waves), so a
+    // 64-bit add claims the slots of both queues in one round trip (two round trips were 7 % of this kernel's stall samples)
+    const unsigned m_alive = __ballot_sync(0xffffffffu, alive), m_shadow = __ballot_sync(0xffffffffu, has_shadow);
+    unsigned long long claimed = 0ull;
+    if (lane == 0 && (m_alive | m_shadow))
+      claimed = atomicAdd(reinterpret_cast<unsigned long long*>(n_out), (unsigned long long)__popc(m_alive) | ((unsigned long long)__popc(m_shadow) << 32));
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    const int pos = (int)(unsigned)(claimed & 0xffffffffull) + __popc(m_alive & lt);
+    const int spos = (int)(unsigned)(claimed >> 32) + __popc(m_shadow & lt);
     if (alive) {
       o0[pos] = make_float4(P.x, P.y, P.z, nd.x);
       o1[pos] = make_float4(nd.y, nd.z, beta.x, beta.y);
       o2[pos] = make_float4(beta.z, bs_pdf, __uint_as_float(rng), __int_as_float(pid));
       if (key_out) key_out[pos] = (uint16_t)sort_key(sc.sort_grid, P, nd);  // for the re-ordering before the next extend (ray_sort.cuh)
     }
-    const int spos = warp_append(n_shadow, has_shadow);
     if (has_shadow) {
       q0[spos] = make_float4(P.x, P.y, P.z, sh_wi.x);
       q1[spos] = make_float4(sh_wi.y, sh_wi.z, sh_tmax, __int_as_float(pid));
@@ -667,6 +692,8 @@ int ensure_wave_buffers(BnScene* s, size_t cap) {
     if (!cuda_ok(e, "cudaMalloc(wave buffers)")) { drop(); return BN_ERR_CUDA; }
   }
   if (!cuda_ok(cudaMemset(s->sort_bins, 0, 2 * kSortBins * sizeof(uint32_t)), "cudaMemset(sort bins)")) { drop(); return BN_ERR_CUDA; }
+  // k_sort_hist reads the keys eight at a time and masks what lies beyond the queue's end: give those lanes defined bytes
+  if (!cuda_ok(cudaMemset(s->sort_key, 0, cap * sizeof(uint16_t)), "cudaMemset(sort keys)")) { drop(); return BN_ERR_CUDA; }
   s->cap = cap;
   return BN_OK;
 }
@@ -783,7 +810,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
         wp.il_count = il_count; wp.il_index = il_index;
         int* base = s->counters + per_wave * (size_t)wave;
         int* n_active = base;                               // [b] at n_active + b * CS, and so on
-        int* n_shadow = base + (size_t)(D + 1) * CS;
+        int* n_shadow = n_active + CS + 1;  // [b]: the int right after n_active[b + 1] — k_shade appends to both queues with one 64-bit atomic
         int* cursors = base + (size_t)((D + 1) + D) * CS;
         int* n_defer = cursors + (size_t)(3 * D) * CS;
         int* n_done = n_defer + (size_t)(2 * D) * CS;
@@ -819,7 +846,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
           prof_end();
           prof_begin(1);
           k_shade<<<s->num_sms * BN_SHADE_MIN_BLOCKS, kBlock, 0, stream>>>(s->d, wp, b, S, S + cp, A + 2 * cp, s->hits, B, B + cp, B + 2 * cp, s->shq, s->shq + cp,
-                                               s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b * CS, n_active + (b + 1) * CS, n_shadow + b * CS,
+                                               s->shq + 2 * cp, s->shq + 3 * cp, s->rad, n_active + b * CS, n_active + (b + 1) * CS,
                                                cursors + (3 * b + 1) * CS, s->shadow_ref, (order_paths && b + 1 < D && b + 1 >= order_from) ? s->sort_key : nullptr, perm);
           prof_end();
           prof_begin(2);
@@ -850,7 +877,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
       for (long long w = 0; w < n_waves; ++w) {
         const int* base = h_counters.data() + per_wave * (size_t)w;
         std::fprintf(stderr, "bn_counts wave %lld:", w);
-        for (int b = 0; b < D; ++b) std::fprintf(stderr, " b%d extend=%d shadow=%d", b, base[(size_t)b * CS], base[(size_t)(D + 1 + b) * CS]);
+        for (int b = 0; b < D; ++b) std::fprintf(stderr, " b%d extend=%d shadow=%d", b, base[(size_t)b * CS], base[(size_t)(b + 1) * CS + 1]);
         std::fprintf(stderr, "\n");
       }
     }
@@ -859,7 +886,7 @@ int render_waves(BnScene* s, const BnRenderParams* p, float* d_film, float* d_ra
       for (long long w = 0; w < n_waves; ++w) {
         const int* base = h_counters.data() + per_wave * (size_t)w;
         n_paths += (uint64_t)base[0];
-        for (int b = 0; b < D; ++b) { ext += (uint64_t)base[(size_t)b * CS]; sh += (uint64_t)base[(size_t)(D + 1 + b) * CS]; }
+        for (int b = 0; b < D; ++b) { ext += (uint64_t)base[(size_t)b * CS]; sh += (uint64_t)base[(size_t)(b + 1) * CS + 1]; }
       }
       unsigned long long ref = 0;
       BN_CUDA(cudaMemcpy(&ref, s->shadow_ref, sizeof ref, cudaMemcpyDeviceToHost));
