@@ -136,15 +136,13 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_rank(const uint16_t* __re
     __syncthreads();
     const int first = tile * kSortTile + threadIdx.x;
     uint32_t kr[kSortPerThread];  // key | rank within the tile's share of the bin << 16
+    // all of a thread's key loads first (unconditional, index clamped: "load, rank, load, rank" would pay sixteen memory
+    // round trips per tile one after the other), then the ranks
 #pragma unroll
-    for (int j = 0; j < kSortPerThread; ++j) {
-      const int i = first + j * kSortThreads;
-      kr[j] = 0u;
-      if (i < n) {
-        const uint32_t k = key[i] & (uint32_t)(kSortBins - 1);
-        kr[j] = k | (atomicAdd(&sh[k], 1u) << 16);
-      }
-    }
+    for (int j = 0; j < kSortPerThread; ++j) kr[j] = key[min(first + j * kSortThreads, n - 1)] & (uint32_t)(kSortBins - 1);
+#pragma unroll
+    for (int j = 0; j < kSortPerThread; ++j)
+      if (first + j * kSortThreads < n) kr[j] |= atomicAdd(&sh[kr[j]], 1u) << 16;
     __syncthreads();
     {
       // all of a thread's claims in flight together: a loop of "atomic, then store its result" issues them one round trip
