@@ -76,6 +76,11 @@ constexpr int kRefillMinAny = BN_REFILL_MIN_ANY;  // ... for any-hit (shadow) ra
                             // phase step of the lanes that still hold a ray in between (the claim stays exact: the lanes idle at the
                             // first vote get the slots)
 #endif
+#ifndef BN_STACK_TOP_REG
+#define BN_STACK_TOP_REG 0   // 1: the top entry of the traversal stack lives in registers; a pop hands it out and starts the load of
+                            // the entry below without waiting for it (the pop's local-memory load was 8-11 % of the ordered
+                            // kernel's stall samples, executed by 2-3 lanes at a time)
+#endif
 #ifndef BN_PREFETCH_AHEAD
 #define BN_PREFETCH_AHEAD 16384
 #endif
@@ -330,6 +335,9 @@ template <> struct TravStack<true> {
 template <bool ANY, bool WIDE, class IO>
 BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __restrict__ cold, const int cold_stride) {
   typename TravStack<ANY>::type stk[kStackSize];
+#if BN_STACK_TOP_REG
+  typename TravStack<ANY>::type top{};  // entry sp - 1 (entries 0 .. sp - 2 are in stk[])
+#endif
   // per-lane state
   float3 wo, winv;        // world-space ray (origin, 1/direction)
   float3 o, d, inv;       // ray in the CURRENT space
@@ -346,6 +354,15 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
   uint32_t signs = 8u;    // dir_signs of the current-space direction
   uint32_t wsigns = 8u;   // ... of the world-space direction
   int sp = 0;
+  auto push_entry = [&](uint32_t ref, float tmin) {
+#if BN_STACK_TOP_REG
+    if (sp > 0) stk[sp - 1] = top;
+    TravStack<ANY>::push(top, ref, tmin);
+#else
+    TravStack<ANY>::push(stk[sp], ref, tmin);
+#endif
+    ++sp;
+  };
   int cur_inst = -1;
   int& index = reinterpret_cast<int*>(cold)[7 * cold_stride];  // queue slot of this ray
   uint32_t tri_k = 0;     // next triangle of the held BLAS leaf
@@ -387,7 +404,13 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         return;
       }
       --sp;
+#if BN_STACK_TOP_REG
+      const typename TravStack<ANY>::type e = top;
+      if (sp > 0) top = stk[sp - 1];  // issued now, needed at the next pop
+      if (TravStack<ANY>::pop(e, t, cur)) break;
+#else
       if (TravStack<ANY>::pop(stk[sp], t, cur)) break;
+#endif
     }
     if ((cur & kTlasBit) && in_obj) {  // tree TLAS: back from a BLAS, restore the world-space ray (d is only read inside a BLAS)
       o = wo; inv = winv;
@@ -576,9 +599,9 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
               pop();
             } else {
               // the first passing child in visiting order is next; the others wait on the stack, nearest on top
-              if (q3 && (q0 || q1 || q2)) { TravStack<ANY>::push(stk[sp], r3 | level, k3); ++sp; }
-              if (q2 && (q0 || q1)) { TravStack<ANY>::push(stk[sp], r2 | level, k2); ++sp; }
-              if (q1 && q0) { TravStack<ANY>::push(stk[sp], r1 | level, k1); ++sp; }
+              if (q3 && (q0 || q1 || q2)) push_entry(r3 | level, k3);
+              if (q2 && (q0 || q1)) push_entry(r2 | level, k2);
+              if (q1 && q0) push_entry(r1 | level, k1);
               cur = (q0 ? r0 : (q1 ? r1 : (q2 ? r2 : r3))) | level;
             }
           }
@@ -602,8 +625,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
             cur = left;
           } else {
             cur = lf ? left : right;
-            TravStack<ANY>::push(stk[sp], lf ? right : left, lf ? sr.tmin : sl.tmin);
-            ++sp;
+            push_entry(lf ? right : left, lf ? sr.tmin : sl.tmin);
           }
         }
         if (__popc(__ballot_sync(kFull, (int)cur >= 0)) < kStayMin) break;

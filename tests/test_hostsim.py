@@ -398,6 +398,15 @@ def test_whole_paths_on_randomised_scenes(hs, lib, oracle_lib, seed, n_instances
 
 
 
+def test_stack_top_in_registers_gives_the_same_hits(root, scene_loader, lib):
+    """-DBN_STACK_TOP_REG=1 (measured on the B200): the top entry of the traversal stack in registers, the pop starting the
+    load of the entry below without waiting for it — same stack discipline, same hits, same any-hit answers."""
+    variant = _build_warp_emulator(root, "_stack_top", ["BN_STACK_TOP_REG=1"])
+    for name in ("cbox_bunny", "material_sweep", "bunny_instanced_small"):
+        _check_persistent_loop(variant, scene_loader(name), 2500, seed=51)
+    _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(52), 120)), 2000, seed=52)
+
+
 def test_split_phase_refill_gives_the_same_hits(root, scene_loader, lib):
     """-DBN_SPLIT_REFILL=1 (measured on the B200): the cursor's atomic issued at one vote, its result used at the
     next, ONE phase step of the lanes that still hold a ray in between; the claim stays exact.  Every ray is traced exactly once
