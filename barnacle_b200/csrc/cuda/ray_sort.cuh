@@ -16,7 +16,7 @@
 //   k_sort_scan   4096 counts -> bin cursors (one CTA)
 //   k_sort_rank   per tile of 4096 paths: shared-memory ranks, ONE global atomic per non-empty bin of the tile claims the
 //                 tile's slice of that bin; writes perm[ordered slot] = queue index
-// The sort proper moves no path: 2 + 2 + 2 B of keys and 4 B of perm per path, 0.17 ms for 33 M paths.  Who pays for reading
+// The sort proper moves no path: 2 + 2 + 2 B of keys and 4 B of perm per path, 0.2 ms for 33 M paths.  Who pays for reading
 // 48-B path records in a scattered order was the question; measured on C2 at 32 spp (63 ms per frame unordered;
 // profiles/r02_ab_session13..17_*.log):
 //   a copy kernel moving the state (all of the queue, or inside 256 Ki-path segments so that the writes stay in L2):
@@ -26,7 +26,8 @@
 //       traversal kernel's scarcest resource (a 16-B gather costs a lane-cycle): extend 31.3 -> 30.2 only  -> 58.8 ms
 //   extend gathers the two planes it needs anyway and leaves them in order, shade gathers the third       -> 56.8 ms  (adopted)
 // (ExtendIO::load and k_shade in kernels.cu).  Ordering the shadow queue the same way loses (shadow 15.2 -> 19.4 ms: the
-// connect's reads become gathers too).  C1 / C2 / C3 / C4 per frame: -0.7 / -9.5 / -9.4 / -4.1 %.
+// connect's reads become gathers too).  Full-size frames with the ordering and what it made worth doing (refill thresholds, key
+// layout per scene, swizzled node chunks, k_shade's claim pipeline): C1 +9 %, C2 +19 %, C3 +16 %, C4 +10 % (profiles/README.md).
 #pragma once
 #include <stdint.h>
 
