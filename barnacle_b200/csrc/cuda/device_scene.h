@@ -177,7 +177,7 @@ struct DScene {
   const GFlatInst* flat_tlas;  // [8][n_inst] or nullptr when n_inst > kFlatTlasMax
   const GWide* wide;           // 4-wide nodes of the fast path (TLAS first, then every mesh), or nullptr: binary fast path
   uint32_t tlas_wroot;         // TLAS root ref in `wide`
-  uint32_t pad_wide;
+  uint32_t refill_min;         // closest-hit refill threshold of the traversal loop for this scene (0: the compile-time default, traverse.cuh)
   GCamera cam;
   SortGrid sort_grid;
 };

@@ -383,6 +383,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
   unsigned pend_mask = 0u;  // lanes that get the slots of the claim in flight (0: none)
   int pend_base = 0;        // lane 0: the atomic's result
 #endif
+  const int refill_min = ANY ? kRefillMinAny : (sc.refill_min != 0u ? (int)sc.refill_min : kRefillMin);  // (per scene: DScene.refill_min)
   const bool scene_fast = sc.all_finite != 0u;
   const bool flat = sc.flat_tlas != nullptr;
   const uint32_t n_inst = sc.n_inst;
@@ -438,7 +439,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
     // scene, and that is what keeps the node records in L1.)
 #if BN_SPLIT_REFILL
     bool claimed_now = false;
-    if (pend_mask == 0u && n_idle != 0 && !exhausted && (n_idle >= (ANY ? kRefillMinAny : kRefillMin) || n_idle == 32)) {
+    if (pend_mask == 0u && n_idle != 0 && !exhausted && (n_idle >= refill_min || n_idle == 32)) {
       pend_mask = __ballot_sync(kFull, cur == kNone);
       if (lane == 0) pend_base = atomicAdd(io.cursor(), n_idle);
       claimed_now = n_idle != 32;  // lanes with a ray left: one phase step while the atomic is in flight
@@ -452,7 +453,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
       const int mine = base + __popc(idle & lt_mask);
       if (((idle >> lane) & 1u) && mine < n) {
 #else
-    if (n_idle != 0 && !exhausted && (n_idle >= (ANY ? kRefillMinAny : kRefillMin) || n_idle == 32)) {
+    if (n_idle != 0 && !exhausted && (n_idle >= refill_min || n_idle == 32)) {
       const unsigned idle = __ballot_sync(kFull, cur == kNone);
       int base = 0;
       if (lane == 0) base = atomicAdd(io.cursor(), n_idle);
