@@ -210,7 +210,7 @@ BN_API int bn_device_count(void);
  * (16-B loads that bypass L1, `iters` sweeps), in GB/s. */
 BN_API int bn_measure_l2_read_gbs(int device, uint64_t bytes, int iters, double* gbs);
 
-/* bn_scene_destroy parks the scene's device buffers (wave queues: up to ~13 GB at the default 64 Mi-path wave, counters,
+/* bn_scene_destroy parks the scene's device buffers (wave queues: up to ~16 GB at the default 64 Mi-path wave, counters,
  * film, the scene arena) per device for the next scene, so that a host which re-creates the scene every frame pays no
  * driver allocation.  This call returns that memory to the driver (device < 0: every device).  Setting the environment
  * variable BN_NO_BUFFER_CACHE disables the parking altogether. */
