@@ -666,7 +666,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
           bool done = false;
           BN_WORK(slab_pass<true>(slab<true>(lo, hi, o, inv), t) ? 95 : 45);
           if (slab_pass<true>(slab<true>(lo, hi, o, inv), t) && tri_test(p0, p1, p2, o, d, t, tp, u, v)) {
-            h_inst = cur_inst; h_prim = (int)tri; h_u = u; h_v = v;
+            h_inst = ANY ? 0 : cur_inst; h_prim = (int)tri; h_u = u; h_v = v;  // (an any-hit query reports a boolean: no instance index to keep)
             if (ANY) { finish(); done = true; }
             else t = tp;
           }
