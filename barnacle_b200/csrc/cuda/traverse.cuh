@@ -352,7 +352,9 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
   h_inst = -1; h_prim = -1; h_u = 0.f; h_v = 0.f;
   uint32_t cur = kNone;   // ref being processed; kScan: next instance of the flat TLAS; kNone: lane idle
   uint32_t signs = 8u;    // dir_signs of the current-space direction
-  uint32_t wsigns = 8u;   // ... of the world-space direction
+  // (the signs of the world-space direction are read off winv when needed — same signs for every ray the fast phases see, whose
+  // direction components are all non-zero — instead of living in a register)
+  auto wsigns_of = [&]() { return dir_signs(winv); };
   int sp = 0;
   auto push_entry = [&](uint32_t ref, float tmin) {
 #if BN_STACK_TOP_REG
@@ -415,7 +417,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
     }
     if ((cur & kTlasBit) && in_obj) {  // tree TLAS: back from a BLAS, restore the world-space ray (d is only read inside a BLAS)
       o = wo; inv = winv;
-      signs = wsigns;
+      signs = wsigns_of();
       in_obj = false;
     }
   };
@@ -472,7 +474,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         io.load(mine, wo, wd, t);
         wdx = wd.x; wdy = wd.y; wdz = wd.z;
         winv = rcp3(wd);
-        wsigns = dir_signs(wd);
+        const uint32_t wsigns = dir_signs(wd);
         o = wo; d = wd; inv = winv; signs = wsigns;
         in_obj = false; cur_inst = -1; sp = 0; tri_k = 0; tl_pos = 0;
         h_inst = -1; h_prim = -1; h_u = 0.f; h_v = 0.f;
@@ -696,7 +698,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         tri_k = 0;
         if (fbits(m2.w)) {
           // identity mesh instance: object space == world space, root box == instance box (passed)
-          o = wo; d = f3(wdx, wdy, wdz); inv = winv; signs = wsigns;
+          o = wo; d = f3(wdx, wdy, wdz); inv = winv; signs = wsigns_of();
           in_obj = true;
           cur_inst = (int)slot;
           cur = blas_root;
@@ -739,7 +741,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
       // nodes changes neither the set nor the order of instances entered.
       BN_STAT(4, nS);
       if (isS) {
-        const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns & 7u) * n_inst);
+        const float4* fp = reinterpret_cast<const float4*>(sc.flat_tlas + (size_t)(wsigns_of() & 7u) * n_inst);
         bool found = false;
         while (tl_pos != 0u) {
           const uint32_t k = (uint32_t)__ffs((int)tl_pos) - 1u;
@@ -777,7 +779,7 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
             if (fbits(b.w) != kNone) {
               // identity mesh instance: what phase E would do (object space == world space, the BLAS
               // root box is this box), done here so that the ray goes straight to its N / T phase
-              o = wo; d = f3(wdx, wdy, wdz); inv = winv; signs = wsigns;
+              o = wo; d = f3(wdx, wdy, wdz); inv = winv; signs = wsigns_of();
               in_obj = true;
               cur_inst = (int)fbits(a.w);
               tri_k = 0;
