@@ -139,6 +139,7 @@ SYMBOLS = {
     "bn_render_pssmlt_device": (C.c_int, [_VP, C.POINTER(BnMltParams), _VP, _VP, C.POINTER(BnMltStats)]),
     "bn_pssmlt_bootstrap": (C.c_int, [_VP, C.POINTER(BnMltParams), _VP]),
     "bn_debug_render_pssmlt_chains": (C.c_int, [_VP, C.POINTER(BnMltParams), _VP, C.POINTER(BnMltStats), _VP]),
+    "bn_debug_order_keys": (C.c_int, [C.c_int, _VP, C.c_uint32, _VP]),
     "bn_film_to_rgba8_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, _VP]),
     "bn_bvh_build": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_uint32, C.POINTER(BnBVHNode), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]),
     "bn_bvh_build_device": (C.c_int, [C.c_int, _VP, C.c_uint32, _VP, C.c_uint32, _VP, _VP, C.POINTER(C.c_float)]),

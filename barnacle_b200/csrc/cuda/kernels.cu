@@ -955,6 +955,39 @@ int bn_measure_l2_read_gbs(int device, uint64_t bytes, int iters, double* gbs) {
   return BN_OK;
 }
 
+// parity-test entry (declared in the header): the ordering's three kernels on a key array of the caller
+int bn_debug_order_keys(int device, const uint16_t* keys, uint32_t n, uint32_t* perm) {
+  if ((n && (!keys || !perm)) || n > (1u << 30)) { bnhost::set_error("bn_debug_order_keys: bad argument"); return BN_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); bnhost::set_error("no CUDA device"); return BN_ERR_NO_DEVICE; }
+  if (n == 0) return BN_OK;
+  BN_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  BN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const size_t padded = ((size_t)n + 31) & ~(size_t)31;  // k_sort_hist reads the keys eight at a time
+  uint16_t* d_key = nullptr;
+  uint32_t *d_perm = nullptr, *d_bins = nullptr;
+  int* d_n = nullptr;
+  int rc = BN_OK;
+  const int n_int = (int)n;
+  if (!cuda_ok(cudaMalloc((void**)&d_key, padded * sizeof(uint16_t)), "cudaMalloc") || !cuda_ok(cudaMalloc((void**)&d_perm, (size_t)n * sizeof(uint32_t)), "cudaMalloc") ||
+      !cuda_ok(cudaMalloc((void**)&d_bins, 2 * kSortBins * sizeof(uint32_t)), "cudaMalloc") || !cuda_ok(cudaMalloc((void**)&d_n, sizeof(int)), "cudaMalloc") ||
+      !cuda_ok(cudaMemset(d_key, 0, padded * sizeof(uint16_t)), "cudaMemset") || !cuda_ok(cudaMemset(d_bins, 0, 2 * kSortBins * sizeof(uint32_t)), "cudaMemset") ||
+      !cuda_ok(cudaMemset(d_perm, 0xFF, (size_t)n * sizeof(uint32_t)), "cudaMemset") ||
+      !cuda_ok(cudaMemcpy(d_key, keys, (size_t)n * sizeof(uint16_t), cudaMemcpyHostToDevice), "copy keys") ||
+      !cuda_ok(cudaMemcpy(d_n, &n_int, sizeof(int), cudaMemcpyHostToDevice), "copy n")) {
+    rc = BN_ERR_CUDA;
+  } else {
+    k_sort_hist<<<sms * 4, kSortThreads>>>(d_key, d_n, d_bins);
+    k_sort_scan<<<1, kSortScanThreads>>>(d_bins, d_bins + kSortBins);
+    k_sort_rank<<<sms * 4, kSortThreads>>>(d_key, d_n, d_bins + kSortBins, d_perm);
+    if (!cuda_ok(cudaGetLastError(), "ordering kernels") || !cuda_ok(cudaMemcpy(perm, d_perm, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost), "copy perm")) rc = BN_ERR_CUDA;
+  }
+  for (void* p : {(void*)d_key, (void*)d_perm, (void*)d_bins, (void*)d_n})
+    if (p) cudaFree(p);
+  return rc;
+}
+
 int bn_release_cached_buffers(int device) {
   std::lock_guard<std::mutex> lock(g_pool_mutex);
   for (size_t k = 0; k < g_pool.size();) {

@@ -330,6 +330,11 @@ BN_API int bn_pssmlt_bootstrap(BnScene* scene, const BnMltParams* params, float*
  * (per_chain_accepted[chain_end - chain_begin], HOST pointer) — what PSSMLT.fs:412 sums into AcceptedMutationCount. */
 BN_API int bn_debug_render_pssmlt_chains(BnScene* scene, const BnMltParams* params, float* film_rgb, BnMltStats* stats, unsigned int* per_chain_accepted);
 
+/* Parity-test entry for the ordering of the live paths between bounces (no counterpart in the reference: csrc/cuda/ray_sort.cuh):
+ * runs the library's own counting sort (histogram, scan, rank) on n 12-bit keys and returns perm[ordered slot] = index
+ * (HOST pointers).  A correct result is a permutation of 0..n-1 along which the keys never decrease. */
+BN_API int bn_debug_order_keys(int device, const uint16_t* keys, uint32_t n, uint32_t* perm);
+
 /* ---- host-side scene builder (stands in for the managed host: JSON schema of
  *      Extensions/Scene/Loader.fs, Scene.Traverse, BVHNode.Build, AliasTable) -- */
 
