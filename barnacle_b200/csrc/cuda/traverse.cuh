@@ -76,6 +76,10 @@ constexpr int kRefillMinAny = BN_REFILL_MIN_ANY;  // ... for any-hit (shadow) ra
                             // phase step of the lanes that still hold a ray in between (the claim stays exact: the lanes idle at the
                             // first vote get the slots)
 #endif
+#ifndef BN_POP2
+#define BN_POP2 0   // 1: closest-hit pops look at the two topmost entries at once (their loads in flight together): a stale entry — its
+                    // entry distance beyond the t found since it was pushed — then costs no second local-memory round trip
+#endif
 #ifndef BN_STACK_TOP_REG
 #define BN_STACK_TOP_REG 0   // 1: the top entry of the traversal stack lives in registers; a pop hands it out and starts the load of
                             // the entry below without waiting for it (the pop's local-memory load was 8-11 % of the ordered
@@ -406,6 +410,15 @@ BN_DEV void traverse_persistent(const DScene& sc, const IO& io, uint32_t* __rest
         else finish();
         return;
       }
+#if BN_POP2
+      if (!ANY && sp >= 2) {
+        const typename TravStack<ANY>::type e1 = stk[sp - 1], e0 = stk[sp - 2];
+        if (TravStack<ANY>::pop(e1, t, cur)) { sp -= 1; break; }
+        sp -= 2;
+        if (TravStack<ANY>::pop(e0, t, cur)) break;
+        continue;
+      }
+#endif
       --sp;
 #if BN_STACK_TOP_REG
       const typename TravStack<ANY>::type e = top;

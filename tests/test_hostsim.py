@@ -407,6 +407,14 @@ def test_stack_top_in_registers_gives_the_same_hits(root, scene_loader, lib):
     _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(52), 120)), 2000, seed=52)
 
 
+def test_two_entry_pop_gives_the_same_hits(root, scene_loader, lib):
+    """-DBN_POP2=1: closest-hit pops look at the two topmost stack entries at once — same stack discipline, same hits."""
+    variant = _build_warp_emulator(root, "_pop2", ["BN_POP2=1"])
+    for name in ("cbox_bunny", "material_sweep", "bunny_instanced_small"):
+        _check_persistent_loop(variant, scene_loader(name), 2500, seed=41)
+    _check_persistent_loop(variant, Scene.LoadString(_random_scene_json(np.random.default_rng(42), 120)), 2000, seed=42)
+
+
 def test_split_phase_refill_gives_the_same_hits(root, scene_loader, lib):
     """-DBN_SPLIT_REFILL=1 (measured on the B200): the cursor's atomic issued at one vote, its result used at the
     next, ONE phase step of the lanes that still hold a ray in between; the claim stays exact.  Every ray is traced exactly once
